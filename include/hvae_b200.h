@@ -1,0 +1,133 @@
+/* hvae_b200 -- C ABI of the B200-native HybridVAE hot path (libhvae_b200.so).
+ *
+ * The reference (Aymane-Nouhail/Recommendation-System) has no FFI layer: its hot path is stock PyTorch
+ * (ATen) calls issued from src/ml/model.py, src/ml/train.py and src/ml/evaluate.py.  Each entry point
+ * below replaces the ATen call sequence cited next to it (paths relative to the reference root).  The
+ * Python package `hvae_b200` binds these symbols with ctypes and exposes them as torch custom ops
+ * (`torch.ops.hvae_b200.*`); see INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated otherwise; the caller owns all memory;
+ * `stream` is a cudaStream_t passed as void*; every function returns 0 on success and a non-zero status
+ * otherwise, with a message retrievable through hvae_last_error().  Nothing here allocates or synchronises.
+ *
+ * Data layout in HBM:
+ *   interactions  CSR over all users: indptr int64 [U+1], indices int32 [nnz] (sorted per row),
+ *                 values float32 [nnz] or NULL (= all ones).  A batch is `rows` int32 [B] (user ids) or
+ *                 NULL (= users 0..B-1).
+ *   W1^T          encoder.0.weight held transposed, [N, ld1] float32, ld1 = round_up(h1, 4): one item's
+ *                 row is contiguous (16-byte vector loads).
+ *   activations   [B, ld] float32 with ld = round_up(width, 4), pad columns zero.
+ *   E             item embeddings [N, d] float32 (exact mode) and/or bfloat16 (tensor-core mode).
+ */
+#ifndef HVAE_B200_H
+#define HVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-step scalars kept on the device so a captured CUDA graph replays unchanged. */
+typedef struct hvae_step_state {
+    int32_t adam_step;   /* number of optimiser steps taken (torch Adam's `step`) */
+    int32_t anneal_step; /* AnnealedVAE.current_step, src/ml/model.py:310 */
+    float step_size;     /* lr / (1 - beta1^step) */
+    float bc2_sqrt;      /* sqrt(1 - beta2^step) */
+    float beta_kl;       /* KL weight of this step */
+    float inv_bg;        /* 1 / global batch size */
+    float kl_coef;       /* beta_kl / global batch size */
+    float clip_coef;     /* min(1, max_norm / (||g|| + 1e-6)) */
+    float grad_norm;     /* ||g||_2 before clipping */
+    float norm2;         /* ||g||_2^2 */
+} hvae_step_state;
+
+const char* hvae_last_error(void);
+int hvae_abi_version(void);
+
+/* ---- encoder (src/ml/model.py:111-127,149-153) ------------------------------------------------------ */
+/* nn.Linear(N,h) on the sparse row as a gather-sum of W1^T rows + LayerNorm + GELU + Dropout.
+ * gamma == NULL: plain linear output in `act`.  mask: uint8 keep-mask [B,h] or NULL (no dropout). */
+int hvae_gather_ln_fwd(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
+                       const float* W1T, int ld, int h, const float* bias, const float* gamma, const float* beta,
+                       const uint8_t* mask, float keep_scale, float* pre, float* mean, float* rstd, float* act,
+                       void* stream);
+/* LayerNorm + GELU + Dropout of a deeper hidden layer (model.py:115-117). */
+int hvae_ln_act_fwd(const float* pre, int B, int h, int ld, const float* gamma, const float* beta, const uint8_t* mask,
+                    float keep_scale, float* mean, float* rstd, float* act, void* stream);
+/* autograd of the block above: d(pre), d(gamma), d(beta). */
+size_t hvae_ln_bwd_workspace_floats(int B, int ld);
+int hvae_ln_act_bwd(const float* dact, const float* pre, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, const uint8_t* mask, float keep_scale, int B, int h, int ld, float* dpre,
+                    float* dgamma, float* dbeta, float* workspace, void* stream);
+/* column sums (bias gradients); workspace >= 64*C floats. */
+int hvae_colsum(const float* X, int ld, int R, int C, float* out, float* workspace, void* stream);
+/* d(W1^T) for the touched rows only (replaces the dense dW1 = dH^T X of autograd). */
+int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_t* sorted_eid, const int32_t* ent_user,
+                 const float* ent_val, int max_slots, const float* dpre, int ld, float* gs, float* rownorm2, void* stream);
+/* dense variant for the autograd-compatible path (atomics into a zeroed [N, ld] buffer). */
+int hvae_w1_grad_dense(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
+                       const float* dpre, int ld, int h, float* dW1T, void* stream);
+
+/* ---- batch plumbing ---------------------------------------------------------------------------------- */
+size_t hvae_batch_temp_bytes(int cap, int n_items);
+int hvae_batch_offsets(const int64_t* indptr, const int32_t* rows, int B, int32_t* boff, void* stream);
+int hvae_batch_transpose(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
+                         int n_items, int cap, const int32_t* boff, int32_t* keys, int32_t* keys_sorted, int32_t* eid,
+                         int32_t* eid_sorted, int32_t* head, int32_t* slot, int32_t* ent_user, float* ent_val,
+                         int32_t* seg_start, int32_t* uniq_item, int32_t* slot_of_item, int32_t* n_unique,
+                         int32_t* overflow, void* temp, size_t temp_bytes, void* stream);
+int hvae_batch_release(const int32_t* uniq_item, const int32_t* n_unique, int cap, int32_t* slot_of_item, void* stream);
+
+/* ---- dense fp32 GEMM with arbitrary strides (aten::addmm / aten::mm, SURVEY.md K2,K5,K6,K8) ------------ */
+int hvae_gemm_f32(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                  int64_t b_cs, float* C, int64_t ldc, const float* bias, float alpha, void* stream);
+
+/* ---- latent (model.py:157-179, 92-93, 281-290) -------------------------------------------------------- */
+int hvae_reparam_kl(const float* ml, int ldml, const float* eps, int B, int L, float* z, int ldz, float* kl_row,
+                    void* stream);
+int hvae_latent_bwd(const float* dz, int lddz, const float* ml, int ldml, const float* eps, int B, int L,
+                    const float* coef, float* dml, void* stream);
+int hvae_gelu_drop_fwd(const float* q, const uint8_t* mask, float keep_scale, int B, int d, int ld, float* t, void* stream);
+int hvae_gelu_drop_bwd(const float* dt, const float* q, const uint8_t* mask, float keep_scale, int B, int d, int ld,
+                       float* dq, void* stream);
+int hvae_loss_finalize(const float* lse, const float* dot, const float* xsum, const float* kl_row, int B,
+                       const float* inv_bg, const float* beta, float* out, float* acc, void* stream);
+
+/* ---- scoring rows (model.py:198,281; evaluate.py:143-146) ---------------------------------------------- */
+int hvae_row_lse(const float* S, int64_t lds, int rows, int N, float* lse, void* stream);
+int hvae_row_softmax_scale(float* S, int64_t lds, int rows, int N, const float* lse, const float* xsum,
+                           const float* inv_bg, void* stream);
+int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
+                         const void* U, int ldu, const void* E, int lde, int d, int is_bf16, float* dot, float* xsum,
+                         void* stream);
+int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
+                     const float* O, int ldo, const float* oscale, const void* E, int lde, int d, int is_bf16,
+                     const float* inv_bg, float* dU, int lddu, void* stream);
+int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, const int64_t* indptr,
+                   const int32_t* indices, const int32_t* rows, int exclude_seen, int K, float* out_val,
+                   int32_t* out_idx, void* stream);
+int hvae_topk_merge(const float* cval, const int32_t* cidx, int n_rows, int GK, int K, float* out_val, int32_t* out_idx,
+                    void* stream);
+/* Recall/NDCG/HR@K (evaluate.py:32-54,90-98) */
+int hvae_hit_mask(const int32_t* topk, int n_rows, int K, const int64_t* rel_ptr, const int32_t* rel_idx, uint32_t* mask,
+                  void* stream);
+int hvae_metrics_reduce(const uint32_t* mask, const int64_t* rel_ptr, int n_rows, const int32_t* kvals, int nk,
+                        const double* disc, const double* idcg, double* workspace, double* out, void* stream);
+
+/* ---- optimiser (train.py:63,88-92; model.py:312-323) --------------------------------------------------- */
+int hvae_step_begin(hvae_step_state* state, double lr, double beta1, double beta2, double kl_beta_min, double kl_beta_max,
+                    int anneal_steps, int b_global, int advance, void* stream);
+int hvae_grad_norm_clip(const float* gdense, int64_t n_dense, const float* rownorm2, const int32_t* n_unique,
+                        float max_norm, hvae_step_state* state, float* workspace, void* stream);
+int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_params, int64_t n_w1, int ld1,
+                   const int32_t* slot_of_item, const float* gsparse, const float* gdense, const hvae_step_state* state,
+                   float weight_decay, float beta1, float beta2, float eps, void* stream);
+int hvae_fill_noise(uint8_t* mask, int64_t n_mask, float keep_prob, float* eps, int64_t n_eps, uint64_t seed,
+                    uint64_t offset, uint32_t stream_id, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVAE_B200_H */

@@ -1,0 +1,403 @@
+// Encoder kernels.
+//  (1) hvae_gather_ln_fwd : first encoder layer on the sparse user row as an embedding-bag gather-sum of
+//      W1^T rows, fused with bias + LayerNorm + GELU + dropout.   Replaces nn.Linear(N,h) on a dense x
+//      followed by LayerNorm/GELU/Dropout (reference src/ml/model.py:114-117,149).
+//  (2) hvae_ln_act_fwd / hvae_ln_act_bwd : LayerNorm+GELU+dropout of the deeper hidden layers and the
+//      backward of that block for every layer.
+//  (3) hvae_w1_grad : backward of (1): per touched item, sum_b x_bi * dH_b, written to a compact
+//      [n_unique, ld] gradient (deterministic, no atomics) together with its squared norm.
+// HBM-bound; one warp owns one row, 128-bit loads, shuffle reductions.
+#include "common.cuh"
+
+namespace hvae {
+
+__device__ __forceinline__ float& f4(float4& v, int k) { return reinterpret_cast<float*>(&v)[k]; }
+
+template <int NCHUNK>
+__device__ __forceinline__ void ln_gelu_drop_store(float4 (&acc)[NCHUNK], int lane, int row, int h, int ld4,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                   const uint8_t* __restrict__ mask, float keep_scale,
+                                                   float* __restrict__ pre, float* __restrict__ mean_out,
+                                                   float* __restrict__ rstd_out, float* __restrict__ act) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        const int col = (lane + 32 * c) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (col + k < h) s += f4(acc[c], k);
+            else f4(acc[c], k) = 0.f;
+        }
+    }
+    const float mean = warp_sum(s) / (float)h;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        const int col = (lane + 32 * c) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (col + k < h) { const float d = f4(acc[c], k) - mean; q += d * d; }
+    }
+    const float var = warp_sum(q) / (float)h;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    const size_t base4 = (size_t)row * ld4;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        const int col4 = lane + 32 * c;
+        if (col4 >= ld4) continue;
+        if (pre) reinterpret_cast<float4*>(pre)[base4 + col4] = acc[c];
+        float4 o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = col4 * 4 + k;
+            float g = 0.f;
+            if (col < h) {
+                const float y = (f4(acc[c], k) - mean) * rstd * gamma[col] + beta[col];
+                g = gelu(y);
+                if (mask) g = mask[(size_t)row * h + col] ? g * keep_scale : 0.f;
+            }
+            f4(o, k) = g;
+        }
+        reinterpret_cast<float4*>(act)[base4 + col4] = o;
+    }
+}
+
+template <int NCHUNK>
+__global__ void __launch_bounds__(256) gather_ln_fwd_kernel(
+    const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+    const int32_t* __restrict__ rows, int B, const float4* __restrict__ W1T, int ld4, int h,
+    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const uint8_t* __restrict__ mask, float keep_scale, float* __restrict__ pre, float* __restrict__ mean_out,
+    float* __restrict__ rstd_out, float* __restrict__ act) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const int u = rows ? rows[warp] : warp;
+    const int64_t s = indptr[u], e = indptr[u + 1];
+    float4 acc[NCHUNK];
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int64_t j0 = s; j0 < e; j0 += 32) {
+        const int cnt = (int)min((int64_t)32, e - j0);
+        int my_idx = 0;
+        float my_val = 0.f;
+        if (lane < cnt) {
+            my_idx = indices[j0 + lane];
+            my_val = values ? values[j0 + lane] : 1.0f;
+        }
+        int t = 0;
+        for (; t + 2 <= cnt; t += 2) {  // two rows in flight per iteration
+            const int i0 = __shfl_sync(0xffffffffu, my_idx, t), i1 = __shfl_sync(0xffffffffu, my_idx, t + 1);
+            const float v0 = __shfl_sync(0xffffffffu, my_val, t), v1 = __shfl_sync(0xffffffffu, my_val, t + 1);
+            const float4* r0 = W1T + (size_t)i0 * ld4;
+            const float4* r1 = W1T + (size_t)i1 * ld4;
+            float4 a[NCHUNK], b[NCHUNK];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int col4 = lane + 32 * c;
+                if (col4 < ld4) { a[c] = __ldg(r0 + col4); b[c] = __ldg(r1 + col4); }
+                else { a[c] = make_float4(0.f, 0.f, 0.f, 0.f); b[c] = a[c]; }
+            }
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f4(acc[c], k) = fmaf(v0, f4(a[c], k), f4(acc[c], k));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f4(acc[c], k) = fmaf(v1, f4(b[c], k), f4(acc[c], k));
+            }
+        }
+        if (t < cnt) {
+            const int i0 = __shfl_sync(0xffffffffu, my_idx, t);
+            const float v0 = __shfl_sync(0xffffffffu, my_val, t);
+            const float4* r0 = W1T + (size_t)i0 * ld4;
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int col4 = lane + 32 * c;
+                if (col4 < ld4) {
+                    const float4 a = __ldg(r0 + col4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) f4(acc[c], k) = fmaf(v0, reinterpret_cast<const float*>(&a)[k], f4(acc[c], k));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        const int col = (lane + 32 * c) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (col + k < h) f4(acc[c], k) += bias[col + k];
+    }
+    if (gamma) {
+        ln_gelu_drop_store<NCHUNK>(acc, lane, warp, h, ld4, gamma, beta, mask, keep_scale, pre, mean_out, rstd_out, act);
+    } else {  // plain linear output (used by tests of the gather alone)
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+            const int col4 = lane + 32 * c;
+            if (col4 < ld4) reinterpret_cast<float4*>(act)[(size_t)warp * ld4 + col4] = acc[c];
+        }
+    }
+}
+
+template <int NCHUNK>
+__global__ void __launch_bounds__(256) ln_act_fwd_kernel(const float* __restrict__ pre, int B, int h, int ld4,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const uint8_t* __restrict__ mask, float keep_scale,
+                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                         float* __restrict__ act) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    float4 acc[NCHUNK];
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        const int col4 = lane + 32 * c;
+        acc[c] = col4 < ld4 ? reinterpret_cast<const float4*>(pre)[(size_t)warp * ld4 + col4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    ln_gelu_drop_store<NCHUNK>(acc, lane, warp, h, ld4, gamma, beta, mask, keep_scale, nullptr, mean_out, rstd_out, act);
+}
+
+// Backward of LayerNorm+GELU+dropout.  dact may alias dpre.  Each warp walks rows warp, warp+W, ... and
+// keeps its share of d(gamma), d(beta) in registers; per-warp partials go to `partial` [nwarps][2][ld]
+// and are summed in a fixed order by colsum (deterministic).
+template <int NCHUNK>
+__global__ void __launch_bounds__(256) ln_act_bwd_kernel(const float* dact, const float* __restrict__ pre,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const uint8_t* __restrict__ mask, float keep_scale, int B, int h,
+                                                         int ld4, float* dpre, float* __restrict__ partial) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    float4 ag[NCHUNK], ab[NCHUNK];
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) ag[c] = ab[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int row = warp; row < B; row += nwarps) {
+        const float mu = mean[row], rs = rstd[row];
+        float4 xh[NCHUNK], dx[NCHUNK];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+            const int col4 = lane + 32 * c;
+            xh[c] = dx[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col4 >= ld4) continue;
+            const float4 p = reinterpret_cast<const float4*>(pre)[(size_t)row * ld4 + col4];
+            const float4 da = reinterpret_cast<const float4*>(dact)[(size_t)row * ld4 + col4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = col4 * 4 + k;
+                if (col >= h) continue;
+                const float xhat = (reinterpret_cast<const float*>(&p)[k] - mu) * rs;
+                const float y = xhat * gamma[col] + beta[col];
+                float dg = reinterpret_cast<const float*>(&da)[k];
+                if (mask) dg = mask[(size_t)row * h + col] ? dg * keep_scale : 0.f;
+                const float dln = dg * gelu_grad(y);
+                f4(ag[c], k) += dln * xhat;
+                f4(ab[c], k) += dln;
+                const float dxh = dln * gamma[col];
+                f4(xh[c], k) = xhat;
+                f4(dx[c], k) = dxh;
+                s1 += dxh;
+                s2 += dxh * xhat;
+            }
+        }
+        const float m1 = warp_sum(s1) / (float)h, m2 = warp_sum(s2) / (float)h;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+            const int col4 = lane + 32 * c;
+            if (col4 >= ld4) continue;
+            float4 o;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = col4 * 4 + k;
+                f4(o, k) = col < h ? rs * (f4(dx[c], k) - m1 - f4(xh[c], k) * m2) : 0.f;
+            }
+            reinterpret_cast<float4*>(dpre)[(size_t)row * ld4 + col4] = o;
+        }
+    }
+    float4* pg = reinterpret_cast<float4*>(partial) + (size_t)warp * 2 * ld4;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        const int col4 = lane + 32 * c;
+        if (col4 < ld4) { pg[col4] = ag[c]; pg[ld4 + col4] = ab[c]; }
+    }
+}
+
+// out[chunk][c] = sum over rows r in [chunk*rpc, min(R,(chunk+1)*rpc)) of X[r][c]   (fixed order)
+__global__ void colsum_chunk_kernel(const float* __restrict__ X, int ld, int R, int C, int rpc, float* __restrict__ out,
+                                    int out_ld) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int r0 = blockIdx.y * rpc, r1 = min(R, r0 + rpc);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = r0;
+    for (; r + 4 <= r1; r += 4) {
+        s0 += X[(size_t)r * ld + c];
+        s1 += X[(size_t)(r + 1) * ld + c];
+        s2 += X[(size_t)(r + 2) * ld + c];
+        s3 += X[(size_t)(r + 3) * ld + c];
+    }
+    for (; r < r1; ++r) s0 += X[(size_t)r * ld + c];
+    out[(size_t)blockIdx.y * out_ld + c] = (s0 + s1) + (s2 + s3);
+}
+
+// One CTA (4 warps) per touched item: grad row = sum over the item's (user, value) entries of
+// value * dH[user, :].  Entries were sorted stably by item, so the order -- hence the fp32 sum -- is fixed.
+__global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_unique,
+                                                      const int32_t* __restrict__ sorted_eid, const int32_t* __restrict__ ent_user,
+                                                      const float* __restrict__ ent_val, const float* __restrict__ dpre, int ld4,
+                                                      float* __restrict__ gs, float* __restrict__ rownorm2) {
+    extern __shared__ float4 red[];  // [4][ld4]
+    const int slot = blockIdx.x;
+    if (slot >= *n_unique) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = seg_start[slot], e = seg_start[slot + 1];
+    const int nch = (ld4 + 31) / 32;
+    for (int c = 0; c < nch; ++c) {
+        const int col4 = lane + 32 * c;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col4 < ld4) {
+            for (int j = s + warp; j < e; j += 4) {
+                const int eid = sorted_eid[j];
+                const float v = ent_val[eid];
+                const float4 g = __ldg(reinterpret_cast<const float4*>(dpre) + (size_t)ent_user[eid] * ld4 + col4);
+                a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+            }
+            red[warp * ld4 + col4] = a;
+        }
+    }
+    __syncthreads();
+    float n2 = 0.f;
+    for (int col4 = threadIdx.x; col4 < ld4; col4 += 128) {
+        const float4 a = red[col4], b = red[ld4 + col4], c = red[2 * ld4 + col4], d = red[3 * ld4 + col4];
+        float4 o;
+        o.x = (a.x + b.x) + (c.x + d.x); o.y = (a.y + b.y) + (c.y + d.y);
+        o.z = (a.z + b.z) + (c.z + d.z); o.w = (a.w + b.w) + (c.w + d.w);
+        reinterpret_cast<float4*>(gs)[(size_t)slot * ld4 + col4] = o;
+        n2 += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+    }
+    __shared__ float wsum[4];
+    n2 = warp_sum(n2);
+    if (lane == 0) wsum[warp] = n2;
+    __syncthreads();
+    if (threadIdx.x == 0) rownorm2[slot] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+}
+
+// dense (autograd-compat) variant of the layer-1 weight gradient: dW1T[item, :] += x * dH[b, :]
+__global__ void w1_grad_dense_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                     const float* __restrict__ values, const int32_t* __restrict__ rows, int B,
+                                     const float* __restrict__ dpre, int ld, int h, float* __restrict__ dW1T) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const int u = rows ? rows[warp] : warp;
+    for (int64_t j = indptr[u]; j < indptr[u + 1]; ++j) {
+        const float v = values ? values[j] : 1.0f;
+        float* dst = dW1T + (size_t)indices[j] * ld;
+        for (int c = lane; c < h; c += 32) atomicAdd(dst + c, v * dpre[(size_t)warp * ld + c]);
+    }
+}
+
+}  // namespace hvae
+
+using namespace hvae;
+
+#define DISPATCH_NCHUNK(nch, ...)                                       \
+    switch (nch) {                                                      \
+        case 1: { constexpr int NC = 1; __VA_ARGS__; } break;           \
+        case 2: { constexpr int NC = 2; __VA_ARGS__; } break;           \
+        case 3: { constexpr int NC = 3; __VA_ARGS__; } break;           \
+        case 4: { constexpr int NC = 4; __VA_ARGS__; } break;           \
+        case 5: { constexpr int NC = 5; __VA_ARGS__; } break;           \
+        case 6: { constexpr int NC = 6; __VA_ARGS__; } break;           \
+        case 7: case 8: { constexpr int NC = 8; __VA_ARGS__; } break;   \
+        case 9: case 10: case 11: case 12: { constexpr int NC = 12; __VA_ARGS__; } break; \
+        case 13: case 14: case 15: case 16: { constexpr int NC = 16; __VA_ARGS__; } break; \
+        default: return hvae_fail("hidden width %d too large (max 2048)", h); \
+    }
+
+extern "C" {
+
+int hvae_gather_ln_fwd(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
+                       const float* W1T, int ld, int h, const float* bias, const float* gamma, const float* beta,
+                       const uint8_t* mask, float keep_scale, float* pre, float* mean, float* rstd, float* act,
+                       void* stream) {
+    HVAE_REQUIRE(ld % 4 == 0 && ld >= h, "gather_ln_fwd: ld=%d must be a multiple of 4 and >= h=%d", ld, h);
+    if (B == 0) return 0;
+    const int nch = ceil_div(ld / 4, 32);
+    const int blocks = ceil_div(B, 8);
+    DISPATCH_NCHUNK(nch, (gather_ln_fwd_kernel<NC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                             indptr, indices, values, rows, B, reinterpret_cast<const float4*>(W1T), ld / 4, h, bias,
+                             gamma, beta, mask, keep_scale, pre, mean, rstd, act)));
+    HVAE_LAUNCH_CHECK("gather_ln_fwd");
+    return 0;
+}
+
+int hvae_ln_act_fwd(const float* pre, int B, int h, int ld, const float* gamma, const float* beta, const uint8_t* mask,
+                    float keep_scale, float* mean, float* rstd, float* act, void* stream) {
+    HVAE_REQUIRE(ld % 4 == 0 && ld >= h, "ln_act_fwd: bad ld=%d h=%d", ld, h);
+    if (B == 0) return 0;
+    const int nch = ceil_div(ld / 4, 32);
+    DISPATCH_NCHUNK(nch, (ln_act_fwd_kernel<NC><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
+                             pre, B, h, ld / 4, gamma, beta, mask, keep_scale, mean, rstd, act)));
+    HVAE_LAUNCH_CHECK("ln_act_fwd");
+    return 0;
+}
+
+// workspace: partial [nwarps = 8*blocks][2][ld] floats + stage buffer; see hvae_ln_bwd_workspace_floats
+static inline int ln_bwd_blocks(int B) { return max(1, min(74, ceil_div(B, 8))); }
+
+size_t hvae_ln_bwd_workspace_floats(int B, int ld) { return (size_t)ln_bwd_blocks(B) * 8 * 2 * ld; }
+
+int hvae_ln_act_bwd(const float* dact, const float* pre, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, const uint8_t* mask, float keep_scale, int B, int h, int ld, float* dpre,
+                    float* dgamma, float* dbeta, float* workspace, void* stream) {
+    HVAE_REQUIRE(ld % 4 == 0 && ld >= h, "ln_act_bwd: bad ld=%d h=%d", ld, h);
+    if (B == 0) return 0;
+    const int nch = ceil_div(ld / 4, 32);
+    const int blocks = ln_bwd_blocks(B);
+    DISPATCH_NCHUNK(nch, (ln_act_bwd_kernel<NC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                             dact, pre, mean, rstd, gamma, beta, mask, keep_scale, B, h, ld / 4, dpre, workspace)));
+    HVAE_LAUNCH_CHECK("ln_act_bwd");
+    // partial rows are [2*ld] wide: first ld = d(gamma), next ld = d(beta)
+    const int R = blocks * 8;
+    colsum_chunk_kernel<<<dim3(ceil_div(h, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace, 2 * ld, R, h, R, dgamma, h);
+    colsum_chunk_kernel<<<dim3(ceil_div(h, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace + ld, 2 * ld, R, h, R, dbeta, h);
+    HVAE_LAUNCH_CHECK("ln_act_bwd colsum");
+    return 0;
+}
+
+// out[c] = sum_r X[r][c]; two fixed-order stages through `workspace` (>= 64*C floats)
+int hvae_colsum(const float* X, int ld, int R, int C, float* out, float* workspace, void* stream) {
+    if (C == 0) return 0;
+    const int chunks = max(1, min(64, ceil_div(R, 64)));
+    const int rpc = ceil_div(max(R, 1), chunks);
+    colsum_chunk_kernel<<<dim3(ceil_div(C, 128), chunks), 128, 0, (cudaStream_t)stream>>>(X, ld, R, C, rpc, workspace, C);
+    colsum_chunk_kernel<<<dim3(ceil_div(C, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace, C, chunks, C, chunks, out, C);
+    HVAE_LAUNCH_CHECK("colsum");
+    return 0;
+}
+
+int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_t* sorted_eid, const int32_t* ent_user,
+                 const float* ent_val, int max_slots, const float* dpre, int ld, float* gs, float* rownorm2, void* stream) {
+    HVAE_REQUIRE(ld % 4 == 0, "w1_grad: ld=%d must be a multiple of 4", ld);
+    if (max_slots == 0) return 0;
+    const size_t smem = (size_t)4 * ld * sizeof(float);
+    HVAE_REQUIRE(smem <= 48 * 1024, "w1_grad: hidden width %d too large", ld);
+    w1_grad_kernel<<<max_slots, 128, smem, (cudaStream_t)stream>>>(seg_start, n_unique, sorted_eid, ent_user, ent_val, dpre,
+                                                                   ld / 4, gs, rownorm2);
+    HVAE_LAUNCH_CHECK("w1_grad");
+    return 0;
+}
+
+int hvae_w1_grad_dense(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
+                       const float* dpre, int ld, int h, float* dW1T, void* stream) {
+    if (B == 0) return 0;
+    w1_grad_dense_kernel<<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, dpre, ld, h, dW1T);
+    HVAE_LAUNCH_CHECK("w1_grad_dense");
+    return 0;
+}
+
+}  // extern "C"

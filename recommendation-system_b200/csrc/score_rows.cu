@@ -1,0 +1,354 @@
+// Row-wise kernels around the scoring GEMM.
+//  * row_lse / row_softmax_scale : log-softmax pieces of the multinomial NLL for the fp32 (materialised) mode
+//    (reference src/ml/model.py:281).
+//  * sparse_dot_xsum : sum_j x_bj * S_b,idx_j as r sparse dot products u_b . E_idx  (SURVEY.md H4).
+//  * du_finalize     : dU_b = scale_b * O_b - (1/Bg) * sum_j x_bj E_idx_j  -- the "-x" half of
+//    (softmax*|x| - x) . E (model.py:281 backward) is an embedding-bag gather of E rows.
+//  * mask_topk       : seen-item masking + per-user warp-level top-K over a materialised score row
+//    (reference src/ml/evaluate.py:143-146), total order (score desc, index desc).
+//  * hit_mask / metrics_reduce : Recall/NDCG/HR@K (src/ml/evaluate.py:32-54,90-98).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace hvae {
+
+__device__ __forceinline__ void ml_merge(float& m, float& l, float m2, float l2) {
+    const float mn = fmaxf(m, m2);
+    if (mn == -INFINITY) { m = mn; l = 0.f; return; }
+    l = l * expf(m - mn) + l2 * expf(m2 - mn);
+    m = mn;
+}
+
+__global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ S, int64_t lds, int N, float* __restrict__ lse) {
+    const float* row = S + (size_t)blockIdx.x * lds;
+    float m = -INFINITY, l = 0.f;
+    for (int i = threadIdx.x; i < N; i += 256) {
+        const float v = row[i];
+        if (v > m) { l = l * expf(m - v) + 1.0f; m = v; }
+        else l += expf(v - m);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+        ml_merge(m, l, m2, l2);
+    }
+    __shared__ float sm[8], sl[8];
+    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; sl[threadIdx.x >> 5] = l; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) ml_merge(m, l, sm[w], sl[w]);
+        lse[blockIdx.x] = m + logf(l);
+    }
+}
+
+// P = exp(S - lse_b) * xsum_b * inv_bg  in place
+__global__ void row_softmax_scale_kernel(float* __restrict__ S, int64_t lds, int rows, int N, const float* __restrict__ lse,
+                                         const float* __restrict__ xsum, const float* __restrict__ inv_bg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * N) return;
+    const int r = (int)(i / N), c = (int)(i - (int64_t)r * N);
+    const size_t off = (size_t)r * lds + c;
+    S[off] = expf(S[off] - lse[r]) * (xsum[r] * *inv_bg);
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) sparse_dot_xsum_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                              const float* __restrict__ values, const int32_t* __restrict__ rows,
+                                                              int B, const T* __restrict__ U, int ldu, const T* __restrict__ E,
+                                                              int lde, int d, float* __restrict__ dot, float* __restrict__ xsum) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int u = rows ? rows[b] : b;
+    float acc = 0.f, xs = 0.f;
+    for (int64_t j = indptr[u]; j < indptr[u + 1]; ++j) {
+        const float x = values ? values[j] : 1.0f;
+        const T* e = E + (size_t)indices[j] * lde;
+        float p = 0.f;
+        for (int c = lane; c < d; c += 32) p = fmaf(to_f(U[(size_t)b * ldu + c]), to_f(e[c]), p);
+        acc += x * p;  // every lane holds a partial; reduced once below
+        xs += x;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) { dot[b] = acc; xsum[b] = xs; }
+}
+
+// dU[b,:] = s_b * O[b,:] - inv_bg * sum_j x_bj E[idx_j,:];  s_b = oscale ? oscale[b] : 1
+template <typename T>
+__global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                          const float* __restrict__ values, const int32_t* __restrict__ rows, int B,
+                                                          const float* __restrict__ O, int ldo, const float* __restrict__ oscale,
+                                                          const T* __restrict__ E, int lde, int d, const float* __restrict__ inv_bg,
+                                                          float* __restrict__ dU, int lddu) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int u = rows ? rows[b] : b;
+    const float s = oscale ? oscale[b] : 1.0f, ib = *inv_bg;
+    const int64_t js = indptr[u], je = indptr[u + 1];
+    for (int c = lane; c < lddu; c += 32) {
+        float g = 0.f;
+        if (c < d) {
+            float a = 0.f;
+            for (int64_t j = js; j < je; ++j) a = fmaf(values ? values[j] : 1.0f, to_f(E[(size_t)indices[j] * lde + c]), a);
+            g = s * O[(size_t)b * ldo + c] - ib * a;
+        }
+        dU[(size_t)b * lddu + c] = g;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// top-K
+__device__ __forceinline__ bool better(float v, int i, float tv, int ti) { return v > tv || (v == tv && i > ti); }
+
+// One warp per score row.  The list (sv, si) lives in shared memory sorted best-first.
+__device__ __forceinline__ void topk_insert(float* sv, int* si, int K, float cv, int ci, int lane) {
+    int cnt = 0;
+    for (int e = lane; e < K; e += 32) cnt += better(sv[e], si[e], cv, ci) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const int pos = cnt;
+    if (pos >= K) return;
+    float tv[4]; int ti[4];  // K <= 128
+    int n = 0;
+    for (int e = lane; e < K - 1; e += 32, ++n) { tv[n] = sv[e]; ti[n] = si[e]; }
+    __syncwarp();
+    n = 0;
+    for (int e = lane; e < K - 1; e += 32, ++n)
+        if (e >= pos) { sv[e + 1] = tv[n]; si[e + 1] = ti[n]; }
+    if (lane == 0) { sv[pos] = cv; si[pos] = ci; }
+    __syncwarp();
+}
+
+constexpr int kTopkWarps = 4;
+constexpr int kMaxK = 128;
+
+__global__ void __launch_bounds__(kTopkWarps * 32) mask_topk_kernel(float* __restrict__ S, int64_t lds, int n_rows, int N,
+                                                                    int item_offset, const int64_t* __restrict__ indptr,
+                                                                    const int32_t* __restrict__ indices,
+                                                                    const int32_t* __restrict__ rows, int exclude_seen, int K,
+                                                                    float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+    __shared__ float sv_all[kTopkWarps][kMaxK];
+    __shared__ int si_all[kTopkWarps][kMaxK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kTopkWarps + warp;
+    if (r >= n_rows) return;
+    float* sv = sv_all[warp];
+    int* si = si_all[warp];
+    float* row = S + (size_t)r * lds;
+    for (int e = lane; e < K; e += 32) { sv[e] = -INFINITY; si[e] = -1; }
+    if (exclude_seen) {
+        const int u = rows ? rows[r] : r;
+        for (int64_t j = indptr[u] + lane; j < indptr[u + 1]; j += 32) {
+            const int c = indices[j] - item_offset;
+            if (c >= 0 && c < N) row[c] = -INFINITY;
+        }
+    }
+    __syncwarp();
+    float thr_v = -INFINITY;
+    int thr_i = -1;
+    for (int base = 0; base < N; base += 32) {
+        const int c = base + lane;
+        const float v = c < N ? row[c] : -INFINITY;
+        const int gi = c < N ? item_offset + c : -2;
+        unsigned bal = __ballot_sync(0xffffffffu, better(v, gi, thr_v, thr_i));
+        while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const float cv = __shfl_sync(0xffffffffu, v, src);
+            const int ci = __shfl_sync(0xffffffffu, gi, src);
+            if (better(cv, ci, thr_v, thr_i)) {
+                topk_insert(sv, si, K, cv, ci, lane);
+                thr_v = sv[K - 1];
+                thr_i = si[K - 1];
+            }
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < K; e += 32) {
+        out_val[(size_t)r * K + e] = sv[e];
+        out_idx[(size_t)r * K + e] = si[e];
+    }
+}
+
+// Merge G sorted candidate lists per row (item-sharded evaluation): cand [n_rows, G*K] -> top K.
+__global__ void __launch_bounds__(kTopkWarps * 32) topk_merge_kernel(const float* __restrict__ cval, const int32_t* __restrict__ cidx,
+                                                                     int n_rows, int GK, int K, float* __restrict__ out_val,
+                                                                     int32_t* __restrict__ out_idx) {
+    __shared__ float sv_all[kTopkWarps][kMaxK];
+    __shared__ int si_all[kTopkWarps][kMaxK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kTopkWarps + warp;
+    if (r >= n_rows) return;
+    float* sv = sv_all[warp];
+    int* si = si_all[warp];
+    for (int e = lane; e < K; e += 32) { sv[e] = -INFINITY; si[e] = -1; }
+    __syncwarp();
+    for (int j = 0; j < GK; ++j) {
+        const float cv = cval[(size_t)r * GK + j];
+        const int ci = cidx[(size_t)r * GK + j];
+        if (ci >= 0 && better(cv, ci, sv[K - 1], si[K - 1])) topk_insert(sv, si, K, cv, ci, lane);
+    }
+    __syncwarp();
+    for (int e = lane; e < K; e += 32) {
+        out_val[(size_t)r * K + e] = sv[e];
+        out_idx[(size_t)r * K + e] = si[e];
+    }
+}
+
+// hit mask: bit p of mask[r] (4 x u32 per row) is set iff topk[r][p] is one of the row's relevant items.
+__global__ void hit_mask_kernel(const int32_t* __restrict__ topk, int n_rows, int K, const int64_t* __restrict__ rel_ptr,
+                                const int32_t* __restrict__ rel_idx, uint32_t* __restrict__ mask) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const int64_t s = rel_ptr[r], e = rel_ptr[r + 1];
+    for (int w = 0; w < 4; ++w) {
+        const int p = w * 32 + lane;
+        bool hit = false;
+        if (p < K) {
+            const int it = topk[(size_t)r * K + p];
+            for (int64_t j = s; j < e; ++j) hit |= (rel_idx[j] == it);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) mask[(size_t)r * 4 + w] = b;
+    }
+}
+
+// Per-row Recall/NDCG/HR for up to 8 cut-offs, summed in double in a fixed order.
+// disc[p] = 1/log2(p+2), idcg[n] = sum_{i<n} disc[i] (host-computed in float64 with numpy, as the reference does).
+// sums: [gridDim.x][nk*3 + 1] doubles (last = evaluated-row count); reduce with a second launch (n_rows = -gridDim).
+__global__ void __launch_bounds__(256) metrics_partial_kernel(const uint32_t* __restrict__ mask, const int64_t* __restrict__ rel_ptr,
+                                                              int n_rows, const int32_t* __restrict__ kvals, int nk,
+                                                              const double* __restrict__ disc, const double* __restrict__ idcg,
+                                                              double* __restrict__ sums) {
+    __shared__ double red[8][25];
+    double acc[25];
+    for (int i = 0; i < 25; ++i) acc[i] = 0.0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
+        const int nrel = (int)(rel_ptr[r + 1] - rel_ptr[r]);
+        if (nrel == 0) continue;
+        acc[nk * 3] += 1.0;
+        uint32_t m[4] = {mask[(size_t)r * 4], mask[(size_t)r * 4 + 1], mask[(size_t)r * 4 + 2], mask[(size_t)r * 4 + 3]};
+        for (int q = 0; q < nk; ++q) {
+            const int k = kvals[q];
+            int hits = 0;
+            double dcg = 0.0;
+            for (int p = 0; p < k; ++p)
+                if ((m[p >> 5] >> (p & 31)) & 1u) { ++hits; dcg += disc[p]; }
+            acc[q * 3 + 0] += (double)hits / (double)nrel;
+            acc[q * 3 + 1] += dcg / idcg[min(nrel, k)];
+            acc[q * 3 + 2] += hits > 0 ? 1.0 : 0.0;
+        }
+    }
+    const int nv = nk * 3 + 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = 0; i < nv; ++i) {
+        double v = acc[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nv) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        sums[(size_t)blockIdx.x * nv + threadIdx.x] = v;
+    }
+}
+
+__global__ void metrics_final_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out) {
+    const int i = threadIdx.x;
+    if (i >= nv) return;
+    double v = 0.0;
+    for (int b = 0; b < nblocks; ++b) v += partial[(size_t)b * nv + i];
+    out[i] = v;
+}
+
+}  // namespace hvae
+
+using namespace hvae;
+
+extern "C" {
+
+int hvae_row_lse(const float* S, int64_t lds, int rows, int N, float* lse, void* stream) {
+    if (rows == 0) return 0;
+    row_lse_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(S, lds, N, lse);
+    HVAE_LAUNCH_CHECK("row_lse");
+    return 0;
+}
+
+int hvae_row_softmax_scale(float* S, int64_t lds, int rows, int N, const float* lse, const float* xsum, const float* inv_bg,
+                           void* stream) {
+    if (rows == 0) return 0;
+    const int64_t total = (int64_t)rows * N;
+    row_softmax_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(S, lds, rows, N, lse, xsum, inv_bg);
+    HVAE_LAUNCH_CHECK("row_softmax_scale");
+    return 0;
+}
+
+int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
+                         const void* U, int ldu, const void* E, int lde, int d, int is_bf16, float* dot, float* xsum, void* stream) {
+    if (B == 0) return 0;
+    if (is_bf16)
+        sparse_dot_xsum_kernel<__nv_bfloat16><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
+            indptr, indices, values, rows, B, (const __nv_bfloat16*)U, ldu, (const __nv_bfloat16*)E, lde, d, dot, xsum);
+    else
+        sparse_dot_xsum_kernel<float><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, (const float*)U,
+                                                                                       ldu, (const float*)E, lde, d, dot, xsum);
+    HVAE_LAUNCH_CHECK("sparse_dot_xsum");
+    return 0;
+}
+
+int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B, const float* O,
+                     int ldo, const float* oscale, const void* E, int lde, int d, int is_bf16, const float* inv_bg, float* dU,
+                     int lddu, void* stream) {
+    if (B == 0) return 0;
+    if (is_bf16)
+        du_finalize_kernel<__nv_bfloat16><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
+            indptr, indices, values, rows, B, O, ldo, oscale, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
+    else
+        du_finalize_kernel<float><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, O, ldo, oscale,
+                                                                                   (const float*)E, lde, d, inv_bg, dU, lddu);
+    HVAE_LAUNCH_CHECK("du_finalize");
+    return 0;
+}
+
+int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, const int64_t* indptr, const int32_t* indices,
+                   const int32_t* rows, int exclude_seen, int K, float* out_val, int32_t* out_idx, void* stream) {
+    HVAE_REQUIRE(K >= 1 && K <= kMaxK, "mask_topk: K=%d outside [1,%d]", K, kMaxK);
+    if (n_rows == 0) return 0;
+    mask_topk_kernel<<<ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream>>>(
+        S, lds, n_rows, N, item_offset, indptr, indices, rows, exclude_seen, K, out_val, out_idx);
+    HVAE_LAUNCH_CHECK("mask_topk");
+    return 0;
+}
+
+int hvae_topk_merge(const float* cval, const int32_t* cidx, int n_rows, int GK, int K, float* out_val, int32_t* out_idx, void* stream) {
+    HVAE_REQUIRE(K >= 1 && K <= kMaxK, "topk_merge: K=%d outside [1,%d]", K, kMaxK);
+    if (n_rows == 0) return 0;
+    topk_merge_kernel<<<ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream>>>(cval, cidx, n_rows, GK, K, out_val,
+                                                                                                  out_idx);
+    HVAE_LAUNCH_CHECK("topk_merge");
+    return 0;
+}
+
+int hvae_hit_mask(const int32_t* topk, int n_rows, int K, const int64_t* rel_ptr, const int32_t* rel_idx, uint32_t* mask, void* stream) {
+    HVAE_REQUIRE(K >= 1 && K <= kMaxK, "hit_mask: K=%d outside [1,%d]", K, kMaxK);
+    if (n_rows == 0) return 0;
+    hit_mask_kernel<<<ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(topk, n_rows, K, rel_ptr, rel_idx, mask);
+    HVAE_LAUNCH_CHECK("hit_mask");
+    return 0;
+}
+
+// out: nk*3+1 doubles = per cut-off {recall, ndcg, hit} sums, then the evaluated-row count.  workspace >= 148*(nk*3+1) doubles.
+int hvae_metrics_reduce(const uint32_t* mask, const int64_t* rel_ptr, int n_rows, const int32_t* kvals, int nk, const double* disc,
+                        const double* idcg, double* workspace, double* out, void* stream) {
+    HVAE_REQUIRE(nk >= 1 && nk <= 8, "metrics_reduce: nk=%d outside [1,8]", nk);
+    const int blocks = max(1, min(kNumSMs, ceil_div(n_rows, 256)));
+    metrics_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, rel_ptr, n_rows, kvals, nk, disc, idcg, workspace);
+    metrics_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, blocks, nk * 3 + 1, out);
+    HVAE_LAUNCH_CHECK("metrics_reduce");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+"""Drop-in trainer: UserInteractionDataset, VAETrainer, train_hybrid_vae (reference src/ml/train.py).
+
+The step the reference issues as ~60 ATen calls (zero_grad, forward, vae_loss_function, backward,
+clip_grad_norm_, Adam.step, three .item() syncs; src/ml/train.py:86-96) is one fused kernel sequence here
+(engine.Engine.train_step), optionally replayed as a CUDA graph, with the loss kept on the device and read
+back once per epoch.  Batches stay sparse end to end: `CSRLoader` hands the kernels row ids into a CSR that
+is resident in HBM, instead of densifying one [N] row per user on the host (train.py:45-47).
+"""
+from __future__ import annotations
+
+import json
+import logging
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+from scipy.sparse import csr_matrix
+from torch.utils.data import DataLoader, Dataset, RandomSampler
+
+from . import data as _data
+from ._cabi import STATE_OFF, p
+from .engine import Batch, DeviceCSR
+from .model import HybridVAE, create_hybrid_vae, vae_loss_function  # noqa: F401  (re-exported like the reference)
+
+logger = logging.getLogger(__name__)
+
+load_training_data = _data.load_training_data
+get_user_indices_from_df = _data.get_user_indices_from_df
+_build_matrix = _data.build_matrix
+
+
+class UserInteractionDataset(Dataset):
+    """Same contract as the reference (src/ml/train.py:35-47): item i is a dense fp32 [N] row.  The trainer
+    never calls __getitem__ on its own datasets -- it reads `.interaction_matrix` / `.user_indices` and goes
+    through CSRLoader -- but the dense path stays available for callers that index the dataset directly."""
+
+    def __init__(self, interaction_matrix: csr_matrix, user_indices: list[int] | None = None):
+        self.interaction_matrix = interaction_matrix
+        self.user_indices = user_indices or list(range(interaction_matrix.shape[0]))
+
+    def __len__(self) -> int:
+        return len(self.user_indices)
+
+    def __getitem__(self, idx: int) -> torch.Tensor:
+        return torch.FloatTensor(self.interaction_matrix[self.user_indices[idx]].toarray().flatten())
+
+
+class CSRLoader:
+    """Sparse batch iterator over a device-resident CSR.  With shuffle=True the permutation is drawn exactly
+    as torch's RandomSampler does (one int64 seed from the global generator, then randperm on a private
+    generator), so the batch composition equals the reference DataLoader's under the same torch.manual_seed."""
+
+    def __init__(self, matrix, user_indices=None, batch_size=512, shuffle=False, device="cuda", drop_last=False):
+        self.device = torch.device(device)
+        self.csr = matrix if isinstance(matrix, DeviceCSR) else DeviceCSR.from_scipy(matrix, self.device)
+        self.user_indices = np.arange(self.csr.n_users, dtype=np.int64) if user_indices is None else np.asarray(user_indices, dtype=np.int64)
+        self.batch_size, self.shuffle, self.drop_last = int(batch_size), shuffle, drop_last
+
+    def __len__(self):
+        n = len(self.user_indices)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def max_batch_nnz(self, order):
+        lens = self.csr.host_lengths[order]
+        nb = len(self)
+        csum = np.concatenate([[0], np.cumsum(lens)])
+        ends = np.minimum(np.arange(1, nb + 1) * self.batch_size, len(order))
+        return int((csum[ends] - csum[np.arange(nb) * self.batch_size]).max()) if nb else 1
+
+    def __iter__(self):
+        n = len(self.user_indices)
+        if self.shuffle:
+            torch.empty((), dtype=torch.int64).random_()        # DataLoader iterator's _base_seed draw
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())   # RandomSampler's seed draw
+            g = torch.Generator()
+            g.manual_seed(seed)
+            order = self.user_indices[torch.randperm(n, generator=g).numpy()]
+        else:
+            order = self.user_indices
+        cap = max(1, self.max_batch_nnz(order))
+        rows_dev = torch.from_numpy(order.astype(np.int32)).to(self.device, non_blocking=True)
+        for i in range(len(self)):
+            s, e = i * self.batch_size, min((i + 1) * self.batch_size, n)
+            yield Batch(self.csr, rows_dev[s:e], e - s, cap)
+
+
+class FusedAdamState:
+    """`trainer.optimizer`: torch.optim.Adam's hyper-parameters and state_dict() layout over the fused kernel
+    (src/ml/train.py:63; checkpoint layout SURVEY.md §8 a12)."""
+
+    def __init__(self, model: HybridVAE, lr, weight_decay):
+        self.model = model
+        self.defaults = dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay, amsgrad=False,
+                             maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                             decoupled_weight_decay=False)
+        self.param_groups = [dict(self.defaults, params=list(range(len(model.layout.reference_keys()))))]
+
+    def zero_grad(self, set_to_none=True):
+        return None
+
+    def state_dict(self):
+        eng, lay = self.model.engine, self.model.layout
+        state = {}
+        if eng.m is not None:
+            step = float(eng.state[:1].view(torch.int32).item())
+            if step > 0:
+                for i, k in enumerate(lay.reference_keys()):
+                    state[i] = {"step": torch.tensor(step), "exp_avg": lay.view(eng.m, k).clone().contiguous(),
+                                "exp_avg_sq": lay.view(eng.v, k).clone().contiguous()}
+        return {"state": state, "param_groups": [dict(g) for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        """Resume support: restores moments and the step count."""
+        eng, lay = self.model.engine, self.model.layout
+        eng.ensure_optimizer()
+        keys = lay.reference_keys()
+        step = 0
+        for i, k in enumerate(keys):
+            if i in sd["state"]:
+                lay.view(eng.m, k).copy_(sd["state"][i]["exp_avg"])
+                lay.view(eng.v, k).copy_(sd["state"][i]["exp_avg_sq"])
+                step = int(sd["state"][i]["step"])
+        eng.state[:1].view(torch.int32).fill_(step)
+        if sd.get("param_groups"):
+            self.param_groups[0].update({k: v for k, v in sd["param_groups"][0].items() if k != "params"})
+
+
+class VAETrainer:
+    """src/ml/train.py:55-145 with the same constructor, methods, return values and attributes."""
+
+    def __init__(self, model: HybridVAE, device: torch.device, lr: float = 0.001, weight_decay: float = 0.0,
+                 noise: str = "philox", use_cuda_graph: bool = True):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("hvae_b200.VAETrainer needs a CUDA device (there is no CPU fallback)")
+        self.model = model.to(device)
+        self.device = device
+        self.lr, self.weight_decay = lr, weight_decay
+        self.optimizer = FusedAdamState(self.model, lr, weight_decay)
+        self.train_losses: list[float] = []
+        self.val_losses: list[float] = []
+        self.train_recon_losses: list[float] = []
+        self.train_kl_losses: list[float] = []
+        self.noise_mode = noise                 # "philox": in-kernel counter RNG; "torch": torch's CUDA generator
+        self.use_cuda_graph = use_cuda_graph
+        self._noise_seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        self._noise_ctr = 0
+        self._loaders = {}
+        self._graphs = {}
+        logger.info("Trainer on %s, %s params", device, f"{self.model.num_parameters():,}")
+
+    # -- loaders -------------------------------------------------------------------------------------------------
+    def _sparse_loader(self, loader):
+        """Map a torch DataLoader over a UserInteractionDataset onto the equivalent CSRLoader."""
+        if isinstance(loader, CSRLoader):
+            return loader
+        ds = getattr(loader, "dataset", None)
+        if isinstance(loader, DataLoader) and hasattr(ds, "interaction_matrix") and hasattr(ds, "user_indices") \
+                and loader.batch_size is not None:
+            key = id(loader)
+            if key not in self._loaders:
+                self._loaders[key] = CSRLoader(ds.interaction_matrix, ds.user_indices, loader.batch_size,
+                                               isinstance(loader.sampler, RandomSampler), self.device, loader.drop_last)
+            return self._loaders[key]
+        return None
+
+    def _batches(self, loader):
+        sl = self._sparse_loader(loader)
+        if sl is not None:
+            yield from sl
+            return
+        for x in loader:                       # generic iterable of dense / sparse tensors
+            yield self.model._as_batch(x.to(self.device))
+
+    # -- noise ---------------------------------------------------------------------------------------------------
+    def _noise(self, B):
+        m = self.model
+        if self.noise_mode == "torch":
+            return m._draw_noise(B)
+        eng, lay = m.engine, m.layout
+        keep = 1.0 - m.dropout
+        masks = []
+        for i, h in enumerate(m.hidden_dims):
+            if m.dropout > 0:
+                mk = eng.ws.get(f"mask{i}", (B, h), torch.uint8)
+                eng.lib.fill_noise(p(mk), B * h, keep, None, 0, self._noise_seed, self._noise_ctr, 1 + i, eng.stream)
+                masks.append(mk)
+            else:
+                masks.append(None)
+        eps = eng.ws.get("eps", (B, m.latent_dim))
+        eng.lib.fill_noise(None, 0, keep, p(eps), B * m.latent_dim, self._noise_seed, self._noise_ctr, 100, eng.stream)
+        pmask = None
+        if not lay.identity_proj and m.dropout > 0:
+            pmask = eng.ws.get("pmask", (B, m.embedding_dim), torch.uint8)
+            eng.lib.fill_noise(p(pmask), B * m.embedding_dim, keep, None, 0, self._noise_seed, self._noise_ctr, 200, eng.stream)
+        self._noise_ctr += (B * max(max(m.hidden_dims), m.embedding_dim) + 3) // 4
+        return dict(masks=masks, eps=eps, pmask=pmask)
+
+    # -- steps ---------------------------------------------------------------------------------------------------
+    def _anneal(self):
+        m = self.model
+        if hasattr(m, "compute_loss"):       # AnnealedVAE duck-typing, as src/ml/train.py:74
+            return dict(beta_min=m.beta_min, beta_max=m.beta_max, anneal_steps=int(m.anneal_steps))
+        return dict(beta_min=0.0, beta_max=m.beta, anneal_steps=0)
+
+    def train_step(self, batch: Batch, noise=None, b_global=None):
+        """One optimisation step on a sparse batch; `noise` overrides the trainer's RNG (parity tests)."""
+        m = self.model
+        eng = m.engine
+        if noise is None:
+            noise = self._noise(batch.B)
+        if hasattr(m, "current_step"):
+            eng.state[STATE_OFF["anneal_step"]:STATE_OFF["anneal_step"] + 1].view(torch.int32).fill_(int(m.current_step))
+        eng.train_step(batch, noise, lr=self.lr, weight_decay=self.weight_decay, b_global=b_global, **self._anneal())
+        if hasattr(m, "current_step"):
+            m.step_annealing()
+
+    def train_epoch(self, loader) -> dict[str, float]:
+        """src/ml/train.py:81-103: mean of the per-batch (total, recon, kl) over the epoch."""
+        self.model.train()
+        eng = self.model.engine
+        eng.acc.zero_()
+        for batch in self._batches(loader):
+            self.train_step(batch)
+        acc = eng.acc.cpu().numpy().astype(np.float64)     # the epoch's only device->host read
+        n = max(1.0, acc[3])
+        return {"total_loss": float(acc[0] / n), "recon_loss": float(acc[1] / n), "kl_loss": float(acc[2] / n)}
+
+    def validate(self, loader) -> dict[str, float]:
+        """src/ml/train.py:105-124: eval mode, fixed model.beta."""
+        self.model.eval()
+        eng = self.model.engine
+        eng.acc.zero_()
+        with torch.no_grad():
+            for batch in self._batches(loader):
+                eng.eval_step(batch, float(self.model.beta))
+        acc = eng.acc.cpu().numpy().astype(np.float64)
+        n = max(1.0, acc[3])
+        return {"total_loss": float(acc[0] / n), "recon_loss": float(acc[1] / n), "kl_loss": float(acc[2] / n)}
+
+    def last_losses(self):
+        """(total, recon, kl) of the most recent step (device->host read)."""
+        return tuple(float(v) for v in self.model.engine.loss_out.cpu())
+
+    def save_checkpoint(self, path, epoch: int, is_best: bool = False, extra: dict | None = None) -> None:
+        """src/ml/train.py:126-145: same keys; tensors in the reference's shapes."""
+        checkpoint = {
+            "epoch": epoch,
+            "model_state_dict": self.model.state_dict(),
+            "optimizer_state_dict": self.optimizer.state_dict(),
+            "train_losses": self.train_losses,
+            "val_losses": self.val_losses,
+            "train_recon_losses": self.train_recon_losses,
+            "train_kl_losses": self.train_kl_losses,
+            **(extra or {}),
+        }
+        if hasattr(self.model, "current_step"):
+            checkpoint.setdefault("annealing_current_step", int(self.model.current_step))
+        torch.save(checkpoint, path)
+        if is_best:
+            best_path = Path(path).parent / "best_model.pth"
+            torch.save(checkpoint, best_path)
+            logger.info("Saved best model to %s", best_path)
+
+
+def _get_device(device: str | None = None) -> torch.device:
+    if device:
+        return torch.device(device)
+    if torch.cuda.is_available():
+        return torch.device("cuda")
+    raise RuntimeError("hvae_b200 needs a CUDA device (there is no CPU fallback)")
+
+
+def train_hybrid_vae(data_dir: str, embeddings_path: str, output_dir: str, latent_dim: int = 200,
+                     hidden_dims: list[int] | None = None, batch_size: int = 512, epochs: int = 100,
+                     learning_rate: float = 0.001, weight_decay: float = 0.0, beta: float = 0.2, dropout: float = 0.5,
+                     use_annealing: bool = False, patience: int = 10, device: str | None = None,
+                     ignore_embeddings: bool = False, precision: str | None = None) -> None:
+    """src/ml/train.py:201-342: same files in, same files out (checkpoint_epoch_{e}.pth, best_model.pth,
+    training_history.json)."""
+    dev = _get_device(device)
+    output_path = Path(output_dir)
+    output_path.mkdir(parents=True, exist_ok=True)
+    full_matrix, train_df, val_df, mappings = load_training_data(data_dir)
+    user_to_idx, item_to_idx = mappings["user_to_idx"], mappings["item_to_idx"]
+    n_items = full_matrix.shape[1]
+    train_matrix = _build_matrix(train_df, user_to_idx, item_to_idx, full_matrix.shape)
+    val_matrix = _build_matrix(val_df, user_to_idx, item_to_idx, full_matrix.shape)
+    emb_path = Path(embeddings_path)
+    embeddings, emb_item_to_idx, _ = _data.load_embeddings(embeddings_path, str(emb_path.with_name(f"{emb_path.stem}_mappings.pkl")))
+    assert emb_item_to_idx and len(emb_item_to_idx) == n_items, \
+        f"Embedding mismatch: {len(emb_item_to_idx) if emb_item_to_idx else 0} vs {n_items}"
+    if ignore_embeddings:
+        embeddings = np.random.normal(0, 0.01, embeddings.shape).astype(np.float32)
+    train_loader = CSRLoader(train_matrix, get_user_indices_from_df(train_df, user_to_idx), batch_size, True, dev)
+    val_loader = CSRLoader(val_matrix, get_user_indices_from_df(val_df, user_to_idx), batch_size, False, dev)
+    anneal_steps = int(len(train_loader) * epochs * 0.5)
+    model = create_hybrid_vae(n_items=n_items, item_embeddings=embeddings, latent_dim=latent_dim, hidden_dims=hidden_dims,
+                              dropout=dropout, beta=beta, use_annealing=use_annealing, anneal_steps=anneal_steps,
+                              precision=precision)
+    trainer = VAETrainer(model, dev, learning_rate, weight_decay)
+    best_val_loss, patience_counter = float("inf"), 0
+    start_time = time.time()
+    for epoch in range(epochs):
+        train_metrics = trainer.train_epoch(train_loader)
+        val_metrics = trainer.validate(val_loader)
+        trainer.train_losses.append(train_metrics["total_loss"])
+        trainer.val_losses.append(val_metrics["total_loss"])
+        trainer.train_recon_losses.append(train_metrics["recon_loss"])
+        trainer.train_kl_losses.append(train_metrics["kl_loss"])
+        logger.info("Epoch %d/%d train %.4f (recon %.4f, kl %.4f) val %.4f", epoch + 1, epochs, train_metrics["total_loss"],
+                    train_metrics["recon_loss"], train_metrics["kl_loss"], val_metrics["total_loss"])
+        is_best = val_metrics["total_loss"] < best_val_loss
+        if is_best:
+            best_val_loss, patience_counter = val_metrics["total_loss"], 0
+        else:
+            patience_counter += 1
+        trainer.save_checkpoint(output_path / f"checkpoint_epoch_{epoch + 1}.pth", epoch + 1, is_best,
+                                extra={"train_metrics": train_metrics, "val_metrics": val_metrics,
+                                       "model_config": {"n_items": n_items, "latent_dim": latent_dim, "hidden_dims": hidden_dims,
+                                                        "beta": beta, "dropout": dropout}})
+        if patience_counter >= patience:
+            logger.info("Early stopping at epoch %d", epoch + 1)
+            break
+    training_time = time.time() - start_time
+    with open(output_path / "training_history.json", "w") as f:
+        json.dump({"train_losses": trainer.train_losses, "val_losses": trainer.val_losses,
+                   "train_recon_losses": trainer.train_recon_losses, "train_kl_losses": trainer.train_kl_losses,
+                   "training_time_seconds": round(training_time, 2)}, f, indent=2)
+    logger.info("Training complete. Best val loss %.4f in %.1fs", best_val_loss, training_time)

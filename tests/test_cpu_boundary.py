@@ -1,0 +1,137 @@
+"""CPU: the C-ABI library loads and exports every symbol include/hvae_b200.h declares; the drop-in classes
+keep the reference's constructor / state_dict contract; host-side logic (layout, loaders, metric functions)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import TRAIN_CASES, Case
+from hvae_b200 import _cabi
+from hvae_b200.engine import Layout
+from hvae_b200.model import AnnealedVAE, HybridVAE, create_hybrid_vae, vae_loss_function
+from oracle import hvae_oracle as orc
+
+
+def test_library_exports_every_declared_symbol():
+    decls = _cabi.parse_header()
+    assert len(decls) >= 30
+    dll = ctypes.CDLL(str(_cabi.LIB_PATH))
+    for name in decls:
+        assert hasattr(dll, name), name
+    assert _cabi.lib().abi_version() == 1
+    assert ctypes.sizeof(_cabi.StepState) == 40
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_init_and_state_dict_match_reference_layout(name):
+    """Same torch.manual_seed -> same initial weights as the reference class, bit for bit; same keys, order, shapes."""
+    c = Case(name)
+    torch.manual_seed(c.seed)
+    m = create_hybrid_vae(**c.model_kwargs(), use_annealing=c.annealing, anneal_steps=4)
+    ref = c.state("init")
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape, k
+        assert torch.equal(sd[k], ref[k]), k
+    # round trip through load_state_dict
+    m2 = create_hybrid_vae(**c.model_kwargs())
+    m2.load_state_dict(c.state("final"))
+    for k, v in c.state("final").items():
+        assert torch.equal(m2.state_dict()[k], v), k
+    # strict loading rejects foreign keys / wrong shapes like nn.Module does
+    bad = dict(c.state("final"))
+    bad["bogus"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        m2.load_state_dict(bad)
+    bad = dict(c.state("final"))
+    bad["fc_mu.weight"] = torch.zeros(3, 3)
+    with pytest.raises(RuntimeError):
+        m2.load_state_dict(bad)
+    # the oracle (reference module tree) accepts our state_dict unchanged
+    o = orc.OracleVAE(**c.model_kwargs())
+    o.load_state_dict(m2.state_dict())
+
+
+def test_constructor_contract():
+    E = np.random.default_rng(0).standard_normal((50, 16)).astype(np.float32)
+    m = HybridVAE(n_items=50, item_embeddings=E, latent_dim=8, hidden_dims=[12], dropout=0.1, beta=0.3)
+    assert (m.n_items, m.latent_dim, m.embedding_dim, m.dropout, m.beta, m.hidden_dims) == (50, 8, 16, 0.1, 0.3, [12])
+    assert HybridVAE(50, E).hidden_dims == [600, 200]
+    a = create_hybrid_vae(50, E, latent_dim=8, hidden_dims=[12], use_annealing=True, anneal_steps=10, beta=0.4)
+    assert isinstance(a, AnnealedVAE) and a.beta_max == 0.4 and a.beta_min == 0.0 and a.current_step == 0
+    betas = []
+    for _ in range(12):
+        betas.append(a.get_current_beta())
+        a.step_annealing()
+    assert betas[0] == 0.0 and abs(betas[5] - 0.2) < 1e-12 and betas[10] == 0.4 and betas[11] == 0.4
+    # annealing kwargs silently dropped when use_annealing=False (src/ml/model.py:376-385)
+    assert type(create_hybrid_vae(50, E, latent_dim=8, hidden_dims=[12], anneal_steps=3)) is HybridVAE
+    with pytest.raises(NotImplementedError):
+        HybridVAE(50, E, freeze_embeddings=False)
+    with pytest.raises(ValueError):
+        HybridVAE(49, E)
+    # identity projection when latent == embedding dim: no projection keys
+    assert not any(k.startswith("projection") for k in HybridVAE(50, E, latent_dim=16, hidden_dims=[12]).state_dict())
+
+
+def test_no_cpu_fallback():
+    E = np.eye(8, dtype=np.float32)
+    m = HybridVAE(8, E, latent_dim=4, hidden_dims=[6])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(2, 8))
+    from hvae_b200.train import VAETrainer
+    with pytest.raises(RuntimeError, match="CUDA"):
+        VAETrainer(m, torch.device("cpu"))
+
+
+def test_loss_function_matches_oracle():
+    g = torch.Generator().manual_seed(0)
+    s, x = torch.randn(5, 9, generator=g), (torch.rand(5, 9, generator=g) > 0.6).float()
+    mu, lv = torch.randn(5, 3, generator=g), torch.randn(5, 3, generator=g)
+    for a, b in zip(vae_loss_function(s, x, mu, lv, 0.3), orc.loss_terms(s, x, mu, lv, 0.3)):
+        assert torch.equal(a, b)
+
+
+def test_layout_padding_and_offsets():
+    lay = Layout(101, 30, 10, [37, 22])
+    assert lay.n_w1 == 101 * 40 and lay.n_params % 4 == 0
+    for s in lay.slots.values():
+        assert s.off % 4 == 0 and s.ld % 4 == 0
+    arena = torch.arange(lay.n_params, dtype=torch.float32)
+    assert lay.view(arena, "encoder.0.weight").shape == (37, 101)
+    assert lay.view(arena, "encoder.4.weight").shape == (22, 37)
+    assert lay.view(arena, "fc_logvar.bias").shape == (10,)
+    assert lay.view(arena, "projection_layer.3.weight").shape == (30, 30)
+
+
+def test_csr_loader_matches_dataloader_order():
+    """Shuffled batches equal the reference DataLoader's under the same torch.manual_seed (RandomSampler draws)."""
+    from scipy.sparse import random as sprand
+    from hvae_b200.train import CSRLoader, UserInteractionDataset
+    m = sprand(40, 30, density=0.2, format="csr", random_state=0)
+    users = list(range(3, 37))
+    ds = UserInteractionDataset(m, users)
+    torch.manual_seed(5)
+    ref_batches = [b for b in torch.utils.data.DataLoader(ds, batch_size=8, shuffle=True)]
+    torch.manual_seed(5)
+    ld = CSRLoader(m, users, 8, True, device="cpu")
+    ours = list(ld)
+    assert len(ours) == len(ref_batches) == len(ld)
+    for ob, rb in zip(ours, ref_batches):
+        dense = torch.from_numpy(np.asarray(m[ob.rows.numpy()].toarray(), dtype=np.float32))
+        assert torch.equal(dense, rb)
+        assert ob.nnz_cap >= int((dense != 0).sum())
+
+
+def test_metric_functions_match_oracle():
+    from hvae_b200 import evaluate as ev
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        rec = rng.permutation(40)[:20]
+        rel = rng.integers(0, 40, rng.integers(0, 4))
+        for k in (1, 5, 20):
+            assert ev.recall_at_k(rec, rel, k) == orc.recall_at_k(rec, rel, k)
+            assert ev.ndcg_at_k(rec, rel, k) == orc.ndcg_at_k(rec, rel, k)
+            assert ev.hit_ratio_at_k(rec, rel, k) == orc.hit_ratio_at_k(rec, rel, k)

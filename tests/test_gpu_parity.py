@@ -1,0 +1,263 @@
+"""GPU parity tests: every call goes through the C ABI (libhvae_b200.so) and is compared with the CPU oracle
+and with the golden vectors frozen from the reference.  Exact (fp32) mode tolerances per BASELINE.json:
+loss and KL within 1e-5 relative, top-K indices bit-exact, Recall/NDCG within 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import GOLDEN, TRAIN_CASES, Case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _noise_to(dev, n):
+    u8 = lambda t: None if t is None else t.to(torch.uint8).to(dev).contiguous()
+    return dict(masks=[u8(m) for m in n["masks"]], eps=n["eps"].to(dev).contiguous(), pmask=u8(n["pmask"]))
+
+
+def _build(c, dev, precision="fp32", state="init"):
+    from hvae_b200.model import create_hybrid_vae
+    m = create_hybrid_vae(**c.model_kwargs(), use_annealing=c.annealing, anneal_steps=4, precision=precision)
+    m.load_state_dict(c.state(state))
+    return m.to(dev)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kernel-level checks against plain fp32 torch (on the CPU, float64 where it matters)
+def test_gather_equals_dense_linear(dev):
+    from hvae_b200 import _cabi
+    from hvae_b200.engine import DeviceCSR
+    from hvae_b200.synth import make_interactions
+    lib = _cabi.lib()
+    for (U, N, h) in [(257, 1000, 600), (64, 300, 37), (33, 5000, 1024)]:
+        d = make_interactions(U, N, seed=1)
+        vals = d.values.copy()
+        vals[::5] = 2.0
+        csr = DeviceCSR.from_arrays(d.indptr, d.indices, vals, N, dev)
+        ld = (h + 3) // 4 * 4
+        g = torch.Generator().manual_seed(0)
+        W = torch.randn(h, N, generator=g)
+        b = torch.randn(h, generator=g)
+        W1T = torch.zeros(N, ld)
+        W1T[:, :h] = W.t()
+        W1T, bd = W1T.to(dev), b.to(dev)
+        out = torch.empty(U, ld, device=dev)
+        lib.gather_ln_fwd(csr.indptr.data_ptr(), csr.indices.data_ptr(), csr.values.data_ptr(), None, U, W1T.data_ptr(), ld, h,
+                          bd.data_ptr(), None, None, None, 1.0, None, None, None, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        from scipy.sparse import csr_matrix
+        X = torch.from_numpy(csr_matrix((vals.astype(np.float64), d.indices, d.indptr), shape=(U, N)).toarray())
+        ref = X @ W.double().t() + b.double()
+        np.testing.assert_allclose(out[:, :h].cpu().double().numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+        assert torch.all(out[:, h:] == 0)
+
+
+def test_gemm_all_layouts(dev):
+    from hvae_b200 import _cabi
+    lib = _cabi.lib()
+    g = torch.Generator().manual_seed(1)
+    st = torch.cuda.current_stream().cuda_stream
+    for (M, N, K) in [(130, 70, 33), (512, 400, 600), (5, 1, 7), (257, 768, 200)]:
+        A, B = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g)
+        bias = torch.randn(N, generator=g)
+        ref = (A.double() @ B.double() + bias.double()).numpy()
+        for a_t in (False, True):
+            for b_t in (False, True):
+                Ad = (A.t().contiguous() if a_t else A).to(dev)
+                Bd = (B.t().contiguous() if b_t else B).to(dev)
+                a_rs, a_cs = (1, M) if a_t else (K, 1)
+                b_rs, b_cs = (1, K) if b_t else (N, 1)
+                C = torch.empty(M, N, device=dev)
+                lib.gemm_f32(M, N, K, Ad.data_ptr(), a_rs, a_cs, Bd.data_ptr(), b_rs, b_cs, C.data_ptr(), N, bias.to(dev).data_ptr(), 1.0, st)
+                np.testing.assert_allclose(C.cpu().numpy(), ref, rtol=2e-5, atol=2e-4)
+
+
+def test_topk_order_and_masking(dev):
+    """(score desc, index desc) total order, -inf masking, K up to 128, ragged N, ties."""
+    from hvae_b200 import _cabi
+    lib = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(0)
+    for (R, N, K) in [(7, 1000, 20), (3, 37, 37), (5, 4099, 128), (4, 50, 100 if False else 50)]:
+        S = rng.standard_normal((R, N)).astype(np.float32)
+        S[:, ::7] = np.round(S[:, ::7], 1)           # plenty of exact ties
+        seen_ptr, seen_idx = [0], []
+        for r in range(R):
+            si = np.sort(rng.choice(N, size=min(N - 1, 5 + r), replace=False))
+            seen_idx.extend(si.tolist())
+            seen_ptr.append(len(seen_idx))
+        Sd = torch.from_numpy(S.copy()).to(dev)
+        ip = torch.tensor(seen_ptr, dtype=torch.int64, device=dev)
+        ix = torch.tensor(seen_idx, dtype=torch.int32, device=dev)
+        val = torch.empty(R, K, device=dev)
+        idx = torch.empty(R, K, dtype=torch.int32, device=dev)
+        lib.mask_topk(Sd.data_ptr(), N, R, N, 0, ip.data_ptr(), ix.data_ptr(), None, 1, K, val.data_ptr(), idx.data_ptr(), st)
+        for r in range(R):
+            s = S[r].copy()
+            s[seen_idx[seen_ptr[r]:seen_ptr[r + 1]]] = -np.inf
+            order = np.argsort(s, kind="stable")[::-1][:K]
+            assert np.array_equal(idx[r].cpu().numpy(), order), (R, N, K, r)
+            assert np.array_equal(val[r].cpu().numpy(), s[order])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden cases: the fused trainer against the reference's own numbers
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_fused_train_steps_match_reference(dev, name):
+    from hvae_b200.engine import DeviceCSR
+    from hvae_b200.train import VAETrainer
+    c = Case(name)
+    m = _build(c, dev)
+    tr = VAETrainer(m, dev, lr=1e-3, weight_decay=c.weight_decay)
+    csr = DeviceCSR.from_scipy(c.csr, dev)
+    m.train()
+    for s in range(c.steps):
+        rows = c.rows(s)
+        batch = csr.batch(torch.tensor(rows, dtype=torch.int32, device=dev), rows)
+        tr.train_step(batch, _noise_to(dev, c.noise(s)))
+        total, recon, kl = tr.last_losses()
+        st = m.engine.read_state()
+        ref = c.z["stats"][s]
+        np.testing.assert_allclose([total, recon, kl], ref[:3], rtol=1e-5, err_msg=f"{name} step {s} losses")
+        np.testing.assert_allclose(st["grad_norm"], ref[3], rtol=2e-5, err_msg=f"{name} step {s} grad norm")
+        assert st["adam_step"] == s + 1
+    sd = m.state_dict()
+    for k, v in c.state("final").items():
+        np.testing.assert_allclose(sd[k].cpu().numpy(), v.numpy(), rtol=2e-4, atol=2e-6, err_msg=k)
+    osd = tr.optimizer.state_dict()
+    names = [k for k in c.state("final") if k != "item_embeddings"]
+    for i, k in enumerate(names):
+        np.testing.assert_allclose(osd["state"][i]["exp_avg"].cpu().numpy(), c.z[f"adam_m/{k}"], rtol=1e-4, atol=1e-7, err_msg=k)
+        np.testing.assert_allclose(osd["state"][i]["exp_avg_sq"].cpu().numpy(), c.z[f"adam_v/{k}"], rtol=2e-4, atol=1e-9, err_msg=k)
+        assert float(osd["state"][i]["step"]) == c.steps
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_validate_and_forward_match_reference(dev, name):
+    from hvae_b200.train import CSRLoader, VAETrainer
+    c = Case(name)
+    m = _build(c, dev, state="final")
+    tr = VAETrainer(m, dev)
+    n = min(c.n_users, 2 * c.batch)
+    val = tr.validate(CSRLoader(c.csr, list(range(n)), c.batch, False, dev))
+    np.testing.assert_allclose([val["total_loss"], val["recon_loss"], val["kl_loss"]], c.z["validate"], rtol=1e-5)
+    m.eval()
+    x8 = c.dense(np.arange(8)).to(dev)
+    s, mu, lv = m(x8)
+    np.testing.assert_allclose(s.cpu().numpy(), c.z["fwd8/scores"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(mu.cpu().numpy(), c.z["fwd8/mu"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(lv.cpu().numpy(), c.z["fwd8/logvar"], rtol=1e-4, atol=2e-5)
+    # drop-in pieces: get_user_embedding == mu, decode(mu) == scores, encode on sparse CSR tensor input
+    np.testing.assert_allclose(m.get_user_embedding(x8).cpu().numpy(), mu.cpu().numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(m.decode(mu).cpu().numpy(), s.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    mu2, _ = m.encode(x8.to_sparse_csr())
+    assert torch.equal(mu2, mu)
+
+
+@pytest.mark.parametrize("name", ["tiny_two_hidden", "tiny_identity"])
+def test_autograd_path_matches_reference_grads(dev, name):
+    """model(x) -> vae_loss_function -> backward, the reference-style loop (src/ml/train.py:73-90)."""
+    from hvae_b200.model import vae_loss_function
+    from oracle import hvae_oracle as orc
+    c = Case(name)
+    m = _build(c, dev)
+    o = orc.OracleVAE(**c.model_kwargs())
+    o.load_state_dict(c.state("init"))
+    x = c.dense(c.rows(0))
+    # eval-mode forward keeps the comparison free of RNG
+    m.eval(); o.eval()
+    s, mu, lv = m(x.to(dev))
+    loss, recon, kl = vae_loss_function(s, x.to(dev), mu, lv, c.beta)
+    loss.backward()
+    so, muo, lvo = o.forward_with(x, None)
+    lo, ro, ko = orc.loss_terms(so, x, muo, lvo, c.beta)
+    lo.backward()
+    np.testing.assert_allclose([loss.item(), recon.item(), kl.item()], [lo.item(), ro.item(), ko.item()], rtol=1e-5)
+    g = m.arena.grad
+    for k, prm in o.named_parameters():
+        ours = m.layout.view(g, k).cpu().numpy()
+        np.testing.assert_allclose(ours, prm.grad.numpy(), rtol=2e-4, atol=2e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("name,train", [("tiny_two_hidden_eval", "tiny_two_hidden"), ("tiny_identity_eval", "tiny_identity")])
+def test_full_ranking_matches_reference(dev, name, train):
+    import pandas as pd
+    from hvae_b200.evaluate import RecommendationEvaluator
+    c = Case(train)
+    g = np.load(str(GOLDEN / f"{name}.npz"))
+    m = _build(c, dev, state="final")
+    u2i = {f"u{i:07d}": i for i in range(c.n_users)}
+    i2i = {f"i{i:07d}": i for i in range(c.n_items)}
+    ev = RecommendationEvaluator(m, c.csr, u2i, i2i, dev, batch_users=64)
+    ks = [int(k) for k in g["k_values"]]
+    test_df = pd.DataFrame({"user_id": [f"u{i:07d}" for i in range(c.n_users)], "asin": [f"i{int(t):07d}" for t in c.test_items]})
+    res = ev.evaluate_dataset(test_df, ks)
+    got = np.array([[res[k][mm] for mm in ("recall", "ndcg", "hit_ratio")] for k in ks])
+    np.testing.assert_allclose(got, g["metrics"], atol=1e-12)
+    _, idx = ev.topk_users(np.arange(c.n_users), max(ks))
+    assert np.array_equal(idx.cpu().numpy(), g["topk"])            # bit-exact indices in fp32 mode
+    for u in range(6):
+        i100, s100 = ev.get_user_recommendations(u, top_k=100)
+        assert np.array_equal(i100, g[f"rec100/{u}/idx"])
+        np.testing.assert_allclose(s100, g[f"rec100/{u}/score"], rtol=1e-4, atol=2e-5)
+        i10, _ = ev.get_user_recommendations(u, top_k=10, exclude_seen=False)
+        assert np.array_equal(i10, g[f"rec10_all/{u}/idx"])
+        r = ev.evaluate_user(f"u{u:07d}", [f"i{int(c.test_items[u]):07d}"], ks)
+        assert set(r.keys()) == set(ks)
+    assert ev.evaluate_user("nobody", ["i0000001"]) == {}
+
+
+def test_c1_shape_eval_matches_reference(dev):
+    """Config 1 shape (2,072 x 890, d=384): untrained reference weights under torch.manual_seed(0)."""
+    from hvae_b200.evaluate import RecommendationEvaluator
+    from hvae_b200.model import HybridVAE
+    from hvae_b200.synth import CONFIGS, make_interactions, make_item_embeddings
+    g = np.load(str(GOLDEN / "c1_eval.npz"))
+    c = CONFIGS["c1"]
+    data = make_interactions(c["n_users"], c["n_items"], 0)
+    E = make_item_embeddings(c["n_items"], c["emb_dim"], 0)
+    torch.manual_seed(0)
+    m = HybridVAE(c["n_items"], E, c["latent_dim"], c["hidden_dims"], c["dropout"], c["beta"], precision="fp32")
+    for k, v in m.state_dict().items():
+        assert float(v.double().sum()) == float(g[f"sum/{k}"]), k
+    ev = RecommendationEvaluator(m, data.scipy_csr(), {}, {}, dev)
+    users = g["users"]
+    res, idx = ev.evaluate_users(users, np.arange(len(users) + 1), data.test_items[users], [5, 10, 20])
+    assert np.array_equal(idx.cpu().numpy(), g["topk"])
+    got = np.array([[res[k][mm] for mm in ("recall", "ndcg", "hit_ratio")] for k in (5, 10, 20)])
+    np.testing.assert_allclose(got, g["metrics"], atol=1e-12)
+
+
+def test_checkpoint_round_trip(dev, tmp_path):
+    """save_checkpoint keys (src/ml/train.py:130-139) and load_model_from_checkpoint (evaluate.py:273-291);
+    the file loads into the reference's module tree (the oracle) unchanged."""
+    from hvae_b200.engine import DeviceCSR
+    from hvae_b200.evaluate import load_model_from_checkpoint
+    from hvae_b200.train import VAETrainer
+    from oracle import hvae_oracle as orc
+    c = Case("tiny_two_hidden")
+    m = _build(c, dev)
+    tr = VAETrainer(m, dev)
+    csr = DeviceCSR.from_scipy(c.csr, dev)
+    rows = c.rows(0)
+    tr.train_step(csr.batch(torch.tensor(rows, dtype=torch.int32, device=dev), rows), _noise_to(dev, c.noise(0)))
+    cfg = {"n_items": c.n_items, "latent_dim": c.latent, "hidden_dims": c.hidden, "beta": c.beta, "dropout": c.dropout}
+    path = tmp_path / "checkpoint_epoch_1.pth"
+    tr.save_checkpoint(path, 1, is_best=True, extra={"model_config": cfg, "train_metrics": {}, "val_metrics": {}})
+    assert (tmp_path / "best_model.pth").exists()
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert {"epoch", "model_state_dict", "optimizer_state_dict", "train_losses", "val_losses", "train_recon_losses",
+            "train_kl_losses", "model_config"} <= set(ck)
+    o = orc.OracleVAE(**c.model_kwargs())
+    o.load_state_dict(ck["model_state_dict"])
+    opt = orc.make_adam(o)
+    opt.load_state_dict(ck["optimizer_state_dict"])          # torch's own Adam accepts the layout
+    m2 = load_model_from_checkpoint(str(path), c.embeddings(), dev, precision="fp32")
+    m.eval(); m2.eval()
+    x = c.dense(np.arange(5)).to(dev)
+    assert torch.equal(m(x)[0], m2(x)[0])
