@@ -104,9 +104,9 @@ class RecommendationEvaluator:
         mask = torch.empty(max(n, 1), 4, dtype=torch.int32, device=dev)
         out = torch.zeros(nk * 3 + 1, dtype=torch.float64, device=dev)
         wsd = torch.empty(148 * (nk * 3 + 1), dtype=torch.float64, device=dev)
+        kv, dd, ii = t(list(k_values), torch.int32), t(disc, torch.float64), t(idcg, torch.float64)   # keep alive until the sync
         eng.lib.hit_mask(p(topk_idx), n, K, p(rp), p(ri), p(mask), eng.stream)
-        eng.lib.metrics_reduce(p(mask), p(rp), n, p(t(list(k_values), torch.int32)), nk, p(t(disc, torch.float64)),
-                               p(t(idcg, torch.float64)), p(wsd), p(out), eng.stream)
+        eng.lib.metrics_reduce(p(mask), p(rp), n, p(kv), nk, p(dd), p(ii), p(wsd), p(out), eng.stream)
         o = out.cpu().numpy()
         cnt = o[-1]
         res = {}

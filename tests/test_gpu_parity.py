@@ -148,7 +148,8 @@ def test_validate_and_forward_match_reference(dev, name):
     np.testing.assert_allclose([val["total_loss"], val["recon_loss"], val["kl_loss"]], c.z["validate"], rtol=1e-5)
     m.eval()
     x8 = c.dense(np.arange(8)).to(dev)
-    s, mu, lv = m(x8)
+    with torch.no_grad():
+        s, mu, lv = m(x8)
     np.testing.assert_allclose(s.cpu().numpy(), c.z["fwd8/scores"], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(mu.cpu().numpy(), c.z["fwd8/mu"], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(lv.cpu().numpy(), c.z["fwd8/logvar"], rtol=1e-4, atol=2e-5)
@@ -260,4 +261,5 @@ def test_checkpoint_round_trip(dev, tmp_path):
     m2 = load_model_from_checkpoint(str(path), c.embeddings(), dev, precision="fp32")
     m.eval(); m2.eval()
     x = c.dense(np.arange(5)).to(dev)
-    assert torch.equal(m(x)[0], m2(x)[0])
+    with torch.no_grad():
+        assert torch.equal(m(x)[0], m2(x)[0])
