@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(1024) batch_offsets_kernel(const int64_t* __re
     for (int base = 0; base < B; base += 1024) {
         const int b = base + threadIdx.x;
         int len = 0;
-        if (b < B) { const int u = rows ? rows[b] : b; len = (int)(indptr[u + 1] - indptr[u]); }
+        if (b < B) { const int u = rows ? rows[b] : b; len = u < 0 ? 0 : (int)(indptr[u + 1] - indptr[u]); }  // u < 0: padding slot
         int incl, total;
         Scan(tmp).InclusiveSum(len, incl, total);
         if (b < B) boff[b + 1] = carry + incl;
@@ -40,6 +40,7 @@ __global__ void expand_kernel(const int64_t* __restrict__ indptr, const int32_t*
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     const int u = rows ? rows[b] : b;
+    if (u < 0) return;  // padding slot of a data-parallel global batch
     const int64_t s = indptr[u];
     const int len = (int)(indptr[u + 1] - s), o = boff[b];
     if (o + len > cap) { if (lane == 0) atomicExch(overflow, 1); return; }

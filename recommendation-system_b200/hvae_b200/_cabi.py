@@ -51,7 +51,15 @@ STATE_WORDS = ctypes.sizeof(StepState) // 4
 STATE_OFF = {name: getattr(StepState, name).offset // 4 for name, _ in StepState._fields_}
 
 
+# Kernels of ours launched per C-ABI call (library-internal CUB passes are not counted); default 1.
+KERNELS_PER_CALL = {"hvae_ln_act_bwd": 3, "hvae_colsum": 2, "hvae_batch_transpose": 4, "hvae_grad_norm_clip": 2,
+                    "hvae_metrics_reduce": 2, "hvae_last_error": 0, "hvae_abi_version": 0,
+                    "hvae_ln_bwd_workspace_floats": 0, "hvae_batch_temp_bytes": 0}
+
+
 class _Lib:
+    launches = 0   # running count of hvae kernels launched through this binding (bench.py's gpu_launches)
+
     def __init__(self):
         if not LIB_PATH.exists():
             raise RuntimeError(f"{LIB_PATH} is missing: build it with `python recommendation-system_b200/build.py` "
@@ -67,10 +75,13 @@ class _Lib:
                 setattr(self, name[5:], fn)
 
     def _checked(self, fn, name):
+        nk = KERNELS_PER_CALL.get(name, 1)
+
         def call(*args):
             rc = fn(*args)
             if rc != 0:
                 raise RuntimeError(f"{name}: {self._dll.hvae_last_error().decode()}")
+            self.launches += nk
         call.__name__ = name
         return call
 

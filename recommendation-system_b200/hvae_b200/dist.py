@@ -1,0 +1,147 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch) -- SURVEY.md §8e.
+
+The reference is single-process; these are the three ways its hot path shards on one 8xB200 box:
+
+* training, data parallel over users (`DataParallel`): every rank holds the full model and the full
+  interaction CSR (38 MB at 1M users).  A global batch is split evenly; each rank runs forward/backward on
+  its users with every mean taken over the GLOBAL batch (src/ml/model.py:281,287), then
+    - all-reduce(sum) of the small dense gradients (LayerNorm, biases, fc_mu/fc_logvar, projection; ~2 MB),
+    - all-gather of d(pre-activation of layer 1) [B_local, h] and of the batch's user ids; every rank then
+      reduces the layer-1 weight gradient of the WHOLE batch locally (deterministic segment sums).  The dense
+      d(W1) [N, h] (480 MB at N=200k) never crosses NVLink.
+  Gradient norm, clip coefficient and the fused Adam step are then identical on every rank.
+* evaluation, item-sharded (`ItemShard` + `sharded_topk`): rank g scores items [lo_g, hi_g) only, keeps a
+  local top-K of (score, global item id), all-gathers K candidates per user and merges G*K -> K.
+* independent trainings (grid sweep): `assign_round_robin`.
+
+Everything here works on CPU tensors with the gloo backend too (tests/test_dist_cpu.py); only the kernels
+behind `Engine` need a GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def split_even(n: int, world: int, rank: int):
+    """[lo, hi) of rank's contiguous share of n units; the first n % world ranks get one extra."""
+    q, r = divmod(n, world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def assign_round_robin(n_units: int, world: int, rank: int):
+    """Unit ids of rank for independent work (grid-search configurations, src/ml/tune.py:241)."""
+    return list(range(rank, n_units, world))
+
+
+class ItemShard:
+    """Contiguous item range owned by a rank in item-sharded evaluation."""
+
+    def __init__(self, n_items: int, world: int, rank: int):
+        self.n_items, self.world, self.rank = n_items, world, rank
+        self.lo, self.hi = split_even(n_items, world, rank)
+
+    def ranges(self):
+        return [split_even(self.n_items, self.world, r) for r in range(self.world)]
+
+
+def gather_candidates(val: torch.Tensor, idx: torch.Tensor, group=None):
+    """All-gather per-rank top-K candidates [B, K] -> ([B, G*K] values, [B, G*K] global ids), rank-major."""
+    world = dist.get_world_size(group)
+    B, K = val.shape
+    gv = torch.empty(world, B, K, dtype=val.dtype, device=val.device)
+    gi = torch.empty(world, B, K, dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(gv, val.contiguous(), group=group)
+    dist.all_gather_into_tensor(gi, idx.contiguous(), group=group)
+    return gv.permute(1, 0, 2).reshape(B, world * K).contiguous(), gi.permute(1, 0, 2).reshape(B, world * K).contiguous()
+
+
+def merge_candidates_host(cval: np.ndarray, cidx: np.ndarray, K: int):
+    """NumPy statement of hvae_topk_merge (total order: score desc, index desc; id < 0 = empty slot).
+    Test infrastructure for the CPU (gloo) tests; the GPU path calls the kernel."""
+    B = cval.shape[0]
+    out_v = np.full((B, K), -np.inf, dtype=np.float32)
+    out_i = np.full((B, K), -1, dtype=np.int32)
+    for b in range(B):
+        ok = cidx[b] >= 0
+        v, i = cval[b][ok], cidx[b][ok]
+        order = np.lexsort((-i.astype(np.int64), -v.astype(np.float64)))[:K]
+        out_v[b, :len(order)], out_i[b, :len(order)] = v[order], i[order]
+    return out_v, out_i
+
+
+def sharded_topk(eng, batch, K: int, shard: ItemShard, exclude_seen: bool = True, group=None):
+    """Item-sharded full ranking: local top-K over the rank's items, all-gather, merge."""
+    from ._cabi import p
+    v, i = eng.topk(batch, K, exclude_seen, shard.lo, shard.hi)
+    if shard.world == 1:
+        return v, i
+    cv, ci = gather_candidates(v, i, group)
+    out_v, out_i = torch.empty_like(v), torch.empty_like(i)
+    eng.lib.topk_merge(p(cv), p(ci), batch.B, shard.world * K, K, p(out_v), p(out_i), eng.stream)
+    return out_v, out_i
+
+
+class DataParallel:
+    """Gradient exchange of data-parallel training; installed as `engine.dist`."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    # -- batch splitting -------------------------------------------------------------------------------------
+    def local_rows(self, global_rows):
+        """This rank's contiguous slice of a global batch of user ids."""
+        lo, hi = split_even(len(global_rows), self.world, self.rank)
+        return global_rows[lo:hi]
+
+    def b_max(self, b_global: int) -> int:
+        return (b_global + self.world - 1) // self.world
+
+    # -- collectives --------------------------------------------------------------------------------------------
+    def gather_rows(self, rows_local: torch.Tensor, b_global: int):
+        """All-gather the user ids of the global batch, padded per rank to b_max with -1 (= no user)."""
+        bm = self.b_max(b_global)
+        send = torch.full((bm,), -1, dtype=torch.int32, device=rows_local.device)
+        send[:rows_local.shape[0]] = rows_local
+        out = torch.empty(self.world * bm, dtype=torch.int32, device=rows_local.device)
+        dist.all_gather_into_tensor(out, send, group=self.group)
+        return out
+
+    def gather_dpre(self, dpre_local: torch.Tensor, b_global: int):
+        """All-gather d(pre-activation of layer 1) rows [B_local, ld] -> [world*b_max, ld] (pad rows zero)."""
+        bm = self.b_max(b_global)
+        ld = dpre_local.shape[1]
+        if dpre_local.shape[0] == bm:
+            send = dpre_local.contiguous()
+        else:
+            send = torch.zeros(bm, ld, dtype=dpre_local.dtype, device=dpre_local.device)
+            send[:dpre_local.shape[0]] = dpre_local
+        out = torch.empty(self.world * bm, ld, dtype=dpre_local.dtype, device=dpre_local.device)
+        dist.all_gather_into_tensor(out, send, group=self.group)
+        return out
+
+    def reduce_dense(self, gd: torch.Tensor):
+        dist.all_reduce(gd, op=dist.ReduceOp.SUM, group=self.group)
+
+    def reduce_losses(self, acc: torch.Tensor):
+        """Per-rank loss sums were scaled by 1/B_global, so the global loss is their sum (acc[3] = step count)."""
+        t = acc[:3].clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        acc[:3] = t
+
+    # -- Engine hook (engine.Engine.train_step) -----------------------------------------------------------------
+    def exchange(self, eng, batch, dpre0):
+        from .engine import Batch
+        b_global = eng.b_global
+        self.reduce_dense(eng.gd)
+        rows = batch.rows
+        if rows is None:
+            raise RuntimeError("data-parallel steps need explicit user ids (batch.rows)")
+        rows_all = self.gather_rows(rows, b_global)
+        dpre_all = self.gather_dpre(dpre0[:batch.B], b_global)
+        cap = batch.nnz_cap_global if getattr(batch, "nnz_cap_global", None) else batch.nnz_cap * self.world
+        return Batch(batch.csr, rows_all, rows_all.shape[0], cap), dpre_all

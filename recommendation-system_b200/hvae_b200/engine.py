@@ -134,8 +134,10 @@ class Workspace:
 class Batch:
     """A batch of users: rows (device int32 or None = 0..B-1) into a device CSR."""
 
-    def __init__(self, csr, rows, B, nnz_cap):
+    def __init__(self, csr, rows, B, nnz_cap, b_global=None, nnz_cap_global=None):
         self.csr, self.rows, self.B, self.nnz_cap = csr, rows, B, nnz_cap
+        # data-parallel steps: size of the global batch this is a slice of, and the nnz bound of that global batch
+        self.b_global, self.nnz_cap_global = b_global, nnz_cap_global
 
 
 class DeviceCSR:
@@ -189,6 +191,24 @@ class DeviceCSR:
         return Batch(self, rows_dev, B, max(1, nnz_cap))
 
 
+class _Span:
+    """CUDA-event pair around a named kernel group on the launching stream (bench / profiling only)."""
+
+    def __init__(self, eng, name):
+        self.eng, self.name = eng, name
+
+    def __enter__(self):
+        if self.eng.prof is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.eng.dev))
+
+    def __exit__(self, *exc):
+        if self.eng.prof is not None:
+            self.b.record(torch.cuda.current_stream(self.eng.dev))
+            self.eng.prof.setdefault(self.name, []).append((self.a, self.b))
+
+
 class Engine:
     ADAM_B1, ADAM_B2, ADAM_EPS, MAX_NORM = 0.9, 0.999, 1e-8, 5.0
 
@@ -208,6 +228,15 @@ class Engine:
         self.slot_of_item = None
         self.dist = None  # set by hvae_b200.dist for data-parallel training
         self._E_bf16 = None
+        self.prof = None  # dict name -> [(start, stop) events] when profiling spans are enabled
+
+    def span(self, name):
+        return _Span(self, name)
+
+    def span_ms(self):
+        """{name: [ms per occurrence]} of the recorded spans (synchronises)."""
+        torch.cuda.synchronize(self.dev)
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in (self.prof or {}).items()}
 
     @property
     def E_bf16(self):
@@ -272,9 +301,10 @@ class Engine:
             mean, rstd = ws.get(f"mean{i}", (B,)), ws.get(f"rstd{i}", (B,))
             mask = None if masks is None else masks[i]
             if i == 0:
-                lib.gather_ln_fwd(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, self.P("encoder.0.weight"),
-                                  ld, hi, self.P("encoder.0.bias"), self.P("encoder.1.weight"), self.P("encoder.1.bias"),
-                                  p(mask), self.keep_scale, p(pre), p(mean), p(rstd), p(act), st)
+                with self.span("gather"):
+                    lib.gather_ln_fwd(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, self.P("encoder.0.weight"),
+                                      ld, hi, self.P("encoder.0.bias"), self.P("encoder.1.weight"), self.P("encoder.1.bias"),
+                                      p(mask), self.keep_scale, p(pre), p(mean), p(rstd), p(act), st)
             else:
                 w = lay.slots[f"encoder.{4 * i}.weight"]
                 self.gemm(B, hi, h[i - 1], p(acts[-1]), r4(h[i - 1]), 1, self.P(f"encoder.{4 * i}.weight"), 1, w.ld,
@@ -355,7 +385,8 @@ class Engine:
         ml = self.encode(batch, masks)
         u = self.latent_and_project(batch.B, ml, None if noise is None else noise["eps"],
                                     None if noise is None else noise.get("pmask"))
-        lse, dot, xsum, O, oscale = self.score_loss(batch, u, want_grad)
+        with self.span("score"):
+            lse, dot, xsum, O, oscale = self.score_loss(batch, u, want_grad)
         self.lib.loss_finalize(p(lse), p(dot), p(xsum), p(self.ws.get("kl_row", (batch.B,))), batch.B, self.state_ptr("inv_bg"),
                                self.state_ptr("beta_kl"), p(self.loss_out), p(self.acc) if accumulate else None, self.stream)
         return ml, u, O, oscale
@@ -459,17 +490,22 @@ class Engine:
         self.ensure_optimizer()
         lib, st, lay = self.lib, self.stream, self.lay
         b_global = batch.B if b_global is None else b_global
+        self.b_global = b_global
         self.begin(b_global, lr, beta_min, beta_max, anneal_steps, advance=True)
         ml, u, O, oscale = self.forward_loss(batch, noise, want_grad=True)
-        self.backward(batch, noise, ml, O, oscale)
+        with self.span("bwd_dense"):
+            self.backward(batch, noise, ml, O, oscale)
         wbatch, dpre0 = batch, self.dpre0
         if self.dist is not None:
-            wbatch, dpre0 = self.dist.exchange(self, batch, dpre0)
-        gs, rn2, n_unique, uniq = self.sparse_w1_grad(wbatch, dpre0)
+            with self.span("exchange"):
+                wbatch, dpre0 = self.dist.exchange(self, batch, dpre0)
+        with self.span("w1grad"):
+            gs, rn2, n_unique, uniq = self.sparse_w1_grad(wbatch, dpre0)
         gn_ws = self.ws.get("gn_ws", (256,))
         lib.grad_norm_clip(p(self.gd), lay.n_dense, p(rn2), p(n_unique), self.MAX_NORM, p(self.state), p(gn_ws), st)
-        lib.adam_step(p(self.arena), p(self.m), p(self.v), lay.n_params, lay.n_w1, r4(lay.hidden[0]), p(self.slot_of_item), p(gs),
-                      p(self.gd), p(self.state), weight_decay, self.ADAM_B1, self.ADAM_B2, self.ADAM_EPS, st)
+        with self.span("adam"):
+            lib.adam_step(p(self.arena), p(self.m), p(self.v), lay.n_params, lay.n_w1, r4(lay.hidden[0]), p(self.slot_of_item), p(gs),
+                          p(self.gd), p(self.state), weight_decay, self.ADAM_B1, self.ADAM_B2, self.ADAM_EPS, st)
         lib.batch_release(p(uniq), p(n_unique), wbatch.nnz_cap, p(self.slot_of_item), st)
 
     def eval_step(self, batch: Batch, beta, b_global=None):

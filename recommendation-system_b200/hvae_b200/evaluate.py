@@ -72,7 +72,7 @@ class RecommendationEvaluator:
         self.device = device
         self.interaction_matrix = interaction_matrix
         self.user_to_idx, self.item_to_idx = user_to_idx, item_to_idx
-        self.n_items = interaction_matrix.shape[1]
+        self.n_items = interaction_matrix.n_items if isinstance(interaction_matrix, DeviceCSR) else interaction_matrix.shape[1]
         self.batch_users = batch_users
         self._csr = interaction_matrix if isinstance(interaction_matrix, DeviceCSR) else DeviceCSR.from_scipy(interaction_matrix, device)
 

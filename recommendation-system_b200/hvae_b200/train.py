@@ -85,6 +85,22 @@ class CSRLoader:
             yield Batch(self.csr, rows_dev[s:e], e - s, cap)
 
 
+class ShardedCSRLoader(CSRLoader):
+    """Data-parallel view of CSRLoader: every rank walks the same global batches (same permutation: seed torch
+    identically on all ranks) and yields its contiguous slice, tagged with the global batch size so that every
+    mean is taken over the global batch (hvae_b200.dist.DataParallel)."""
+
+    def __init__(self, matrix, user_indices=None, batch_size=512, shuffle=False, device="cuda", drop_last=False, dp=None):
+        super().__init__(matrix, user_indices, batch_size, shuffle, device, drop_last)
+        self.dp = dp
+
+    def __iter__(self):
+        from .dist import split_even
+        for b in super().__iter__():
+            lo, hi = split_even(b.B, self.dp.world, self.dp.rank)
+            yield Batch(b.csr, b.rows[lo:hi], hi - lo, b.nnz_cap, b_global=b.B, nnz_cap_global=b.nnz_cap)
+
+
 class FusedAdamState:
     """`trainer.optimizer`: torch.optim.Adam's hyper-parameters and state_dict() layout over the fused kernel
     (src/ml/train.py:63; checkpoint layout SURVEY.md §8 a12)."""
@@ -149,6 +165,15 @@ class VAETrainer:
         self._loaders = {}
         self._graphs = {}
         logger.info("Trainer on %s, %s params", device, f"{self.model.num_parameters():,}")
+
+    # -- multi-GPU ---------------------------------------------------------------------------------------------
+    def enable_data_parallel(self, group=None):
+        """Data-parallel training over torch.distributed (NCCL): see hvae_b200.dist.DataParallel."""
+        from .dist import DataParallel
+        dp = DataParallel(group)
+        self.model.engine.dist = dp
+        self._noise_seed = (self._noise_seed + 0x9E3779B97F4A7C15 * (dp.rank + 1)) & 0x7FFFFFFFFFFFFFFF
+        return dp
 
     # -- loaders -------------------------------------------------------------------------------------------------
     def _sparse_loader(self, loader):
@@ -216,13 +241,39 @@ class VAETrainer:
         if hasattr(m, "current_step"):
             m.step_annealing()
 
+    def _host_batch(self, x) -> Batch:
+        """HOST (ideally pinned) or device batch -> device Batch.  Sparse CSR tensors are copied as their three
+        arrays (a few KB per step); dense [B,N] rows are copied whole and compacted on the device."""
+        if isinstance(x, Batch):
+            return x
+        if isinstance(x, torch.Tensor) and x.layout == torch.sparse_csr:
+            crow, col, val = x.crow_indices(), x.col_indices(), x.values()
+            nnz = int(col.shape[0])
+            dev = self.device
+            crow_d = crow.to(dev, torch.int64, non_blocking=True)
+            col_d = (col if col.dtype == torch.int32 else col.to(torch.int32)).to(dev, non_blocking=True)
+            val_d = (val if val.dtype == torch.float32 else val.float()).to(dev, non_blocking=True)
+            csr = DeviceCSR(crow_d, col_d, val_d, x.shape[0], x.shape[1], None)
+            return Batch(csr, None, x.shape[0], max(1, nnz))
+        return self.model._as_batch(x.to(self.device, non_blocking=True))
+
+    def train_on_batch(self, x, b_global=None) -> dict[str, float]:
+        """One iteration of the reference loop (src/ml/train.py:86-96) on one batch: host->device copy of the
+        batch, the fused step, and the three loss scalars read back (the reference's three .item() calls)."""
+        self.model.train()
+        self.train_step(self._host_batch(x), b_global=b_global)
+        total, recon, kl = self.last_losses()
+        return {"total_loss": total, "recon_loss": recon, "kl_loss": kl}
+
     def train_epoch(self, loader) -> dict[str, float]:
         """src/ml/train.py:81-103: mean of the per-batch (total, recon, kl) over the epoch."""
         self.model.train()
         eng = self.model.engine
         eng.acc.zero_()
         for batch in self._batches(loader):
-            self.train_step(batch)
+            self.train_step(batch, b_global=getattr(batch, "b_global", None))
+        if eng.dist is not None:
+            eng.dist.reduce_losses(eng.acc)
         acc = eng.acc.cpu().numpy().astype(np.float64)     # the epoch's only device->host read
         n = max(1.0, acc[3])
         return {"total_loss": float(acc[0] / n), "recon_loss": float(acc[1] / n), "kl_loss": float(acc[2] / n)}
