@@ -116,6 +116,21 @@ int hvae_hit_mask(const int32_t* topk, int n_rows, int K, const int64_t* rel_ptr
 int hvae_metrics_reduce(const uint32_t* mask, const int64_t* rel_ptr, int n_rows, const int32_t* kvals, int nk,
                         const double* disc, const double* idcg, double* workspace, double* out, void* stream);
 
+/* ---- tensor-core scoring, bf16 mode (model.py:198,281; evaluate.py:125-147) ------------------------------ */
+/* S = U E^T on tcgen05 (TMA-fed, TMEM accumulators); the [B,N] scores never reach HBM.  U: bf16 [B, ldu],
+ * E: bf16 [N, lde]; ldu, lde multiples of 8, columns d..ld zero. */
+int hvae_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst_bf16, int ld_dst, void* stream);
+size_t hvae_tc_n_splits(int B, int N);
+/* lse[b] = log sum_i exp(S_bi).  workspace >= 2 * B * hvae_tc_n_splits(B,N) floats. */
+int hvae_tc_score_lse(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* lse, float* workspace,
+                      void* stream);
+/* per item split, the K best (score, global item id) of every user with the user's seen items excluded
+ * (indptr == NULL: nothing excluded).  cand_val / cand_idx: [B, hvae_tc_n_splits(B,N) * K]; reduce with
+ * hvae_topk_merge.  K <= 32.  E points at the first item of the shard, item_offset is its global id. */
+int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, int N, int d, int item_offset,
+                       const int64_t* indptr, const int32_t* indices, const int32_t* rows, int K, float* cand_val,
+                       int32_t* cand_idx, void* stream);
+
 /* ---- optimiser (train.py:63,88-92; model.py:312-323) --------------------------------------------------- */
 int hvae_step_begin(hvae_step_state* state, double lr, double beta1, double beta2, double kl_beta_min, double kl_beta_max,
                     int anneal_steps, int b_global, int advance, void* stream);

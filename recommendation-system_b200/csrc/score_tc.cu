@@ -1,0 +1,374 @@
+// Tensor-core scoring (bf16 mode): S = U E^T on tcgen05 with TMA-fed shared memory and TMEM accumulators; the
+// [B, N] score matrix never leaves the SM.  Replaces decode() + log_softmax of the reference
+// (src/ml/model.py:198,281) and the score -> mask -> argsort loop of the evaluator (src/ml/evaluate.py:125-147).
+//
+//   hvae_tc_score_lse  : per-user log-sum-exp over all items (validation loss / forward of the NLL)
+//   hvae_tc_score_topk : per-user top-K over all (or a shard of the) items with seen-item masking
+//
+// Kernel shape (one CTA = 128 users x a contiguous range of 256-item tiles, 192 threads):
+//   warp 0      TMA producer : U k-block [128 x 64] + E k-block [256 x 64] (bf16, 128B swizzle) per pipeline stage
+//   warp 1      MMA issuer   : tcgen05.mma 128x256x16, fp32 accumulators in TMEM, two accumulator buffers
+//   warps 2..5  epilogue     : tcgen05.ld -> registers; thread <-> user row, so every reduction is thread-local
+// Roofline: tensor pipe (2*128*256*d flop per tile); HBM traffic is E once (L2 serves the re-reads across user tiles).
+#include <cfloat>
+
+#include "common.cuh"
+#include "hvae_b200.h"
+#include "tc_common.cuh"
+
+namespace hvae {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int MAXK_TC = 32;  // top-K list per row kept in shared memory
+constexpr float kLog2e = 1.4426950408889634f;
+
+enum Mode { MODE_LSE = 0, MODE_TOPK = 1 };
+
+struct StatsParams {
+    int B, N, d;          // users in this launch, items in this launch (shard), embedding dim
+    int tiles_per_split;  // 256-item tiles per CTA along the item axis
+    int n_splits;
+    int item_offset;      // global id of item 0 of E (item-sharded evaluation)
+    // MODE_LSE
+    float* part_m;        // [B, n_splits]
+    float* part_l;
+    // MODE_TOPK
+    int K;
+    float* cand_val;      // [B, n_splits * K]
+    int32_t* cand_idx;
+    const int64_t* indptr;   // seen items (CSR over users), may be null
+    const int32_t* indices;
+    const int32_t* rows;     // user ids of the batch rows (null = identity)
+};
+
+struct __align__(8) PipeBarriers {
+    uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ bool better(float v, int i, float tv, int ti) { return v > tv || (v == tv && i > ti); }
+
+template <int MODE>
+__global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_constant__ CUtensorMap tmU,
+                                                             const __grid_constant__ CUtensorMap tmE, StatsParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + STAGES * STAGE_BYTES);
+    float* list_v = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);           // [128][K]   (TOPK)
+    int* list_i = reinterpret_cast<int*>(list_v + BM * MAXK_TC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, split = blockIdx.y;
+    const int n_tiles_total = (P.N + BN - 1) / BN;
+    const int t0 = split * P.tiles_per_split, t1 = min(n_tiles_total, t0 + P.tiles_per_split);
+    const int KB = (P.d + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmU);
+        tma_prefetch_desc(&tmE);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = t0; t < t1; ++t)
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&bars->full[s], STAGE_BYTES);
+                    tma_load_2d(smem + s * STAGE_BYTES, &tmU, kb * BK, m_tile * BM, &bars->full[s]);
+                    tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &tmE, kb * BK, t * BN, &bars->full[s]);
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+            int it = 0;
+            for (int t = t0, ti = 0; t < t1; ++t, ++ti) {
+                const int acc = ti & 1;
+                mbar_wait(&bars->tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&bars->full[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_ss(tmem_base + acc * BN, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc,
+                                (kb | k) != 0);
+                    }
+                    umma_commit(&bars->empty[s]);
+                }
+                umma_commit(&bars->tmem_full[acc]);
+            }
+        }
+    } else {
+        // ---- epilogue: thread <-> user row ------------------------------------------------------------------
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r_local = q * 32 + lane;
+        const int row = m_tile * BM + r_local;
+        const bool row_ok = row < P.B;
+        float m_run = -INFINITY, l_run = 0.f;
+        // top-K state
+        float thr_v = -INFINITY;
+        int thr_i = -1, thr_pos = 0, cnt = 0;
+        float* lv = list_v + r_local * MAXK_TC;
+        int* li = list_i + r_local * MAXK_TC;
+        int64_t seen_p = 0, seen_e = 0;
+        int next_seen = INT_MAX;
+        if (MODE == MODE_TOPK) {
+            for (int e = 0; e < P.K; ++e) { lv[e] = -INFINITY; li[e] = -1; }
+            if (row_ok && P.indptr) {
+                const int u = P.rows ? P.rows[row] : row;
+                seen_p = P.indptr[u];
+                seen_e = P.indptr[u + 1];
+                // first seen item at or after this CTA's first item
+                const int first = P.item_offset + t0 * BN;
+                int64_t lo = seen_p, hi = seen_e;
+                while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (P.indices[mid] < first) lo = mid + 1; else hi = mid; }
+                seen_p = lo;
+                next_seen = seen_p < seen_e ? P.indices[seen_p] : INT_MAX;
+            }
+        }
+        for (int t = t0, ti = 0; t < t1; ++t, ++ti) {
+            const int acc = ti & 1;
+            mbar_wait(&bars->tmem_full[acc], (ti >> 1) & 1);
+            tc_fence_after();
+            const int col0 = t * BN;
+            const int n_valid = min(BN, P.N - col0);
+            // seen items of this row inside the tile (TOPK): local columns, at most 16 tracked exactly
+            int mcol[16];
+            int nmask = 0;
+            if (MODE == MODE_TOPK) {
+                const int tile_end = P.item_offset + col0 + BN;
+                while (next_seen < tile_end) {
+                    if (nmask < 16) mcol[nmask] = next_seen - P.item_offset - col0;
+                    ++nmask;
+                    ++seen_p;
+                    next_seen = seen_p < seen_e ? P.indices[seen_p] : INT_MAX;
+                }
+            }
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, v);
+                tmem_ld_wait();
+                if (c * 32 >= n_valid) continue;
+                if (MODE == MODE_LSE) {
+                    if (c * 32 + 32 > n_valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j >= n_valid) v[j] = -INFINITY;
+                    }
+                    float cm = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
+                    const float m_new = fmaxf(m_run, cm);
+                    const float ms = m_new * kLog2e;
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s += exp2f(fmaf(v[j], kLog2e, -ms));
+                    l_run = l_run * exp2f((m_run - m_new) * kLog2e) + s;
+                    m_run = m_new;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = v[j];
+                        if (x >= thr_v && c * 32 + j < n_valid) {
+                            const int lc = c * 32 + j, gi = P.item_offset + col0 + lc;
+                            bool ok = cnt < P.K || better(x, gi, thr_v, thr_i);
+                            if (ok && nmask) {
+                                if (nmask <= 16) {
+                                    for (int e = 0; e < nmask; ++e) ok &= (mcol[e] != lc);
+                                } else {  // rare: many seen items in one tile -> exact binary search in the row's CSR slice
+                                    const int u = P.rows ? P.rows[row] : row;
+                                    int64_t lo = P.indptr[u], hi = P.indptr[u + 1];
+                                    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (P.indices[mid] < gi) lo = mid + 1; else hi = mid; }
+                                    ok = !(lo < P.indptr[u + 1] && P.indices[lo] == gi);
+                                }
+                            }
+                            if (ok && row_ok) {
+                                int pos = thr_pos;
+                                if (cnt < P.K) pos = cnt++;
+                                lv[pos] = x;
+                                li[pos] = gi;
+                                if (cnt == P.K) {  // recompute the list's worst element (= threshold)
+                                    float wv = lv[0]; int wi = li[0], wp = 0;
+                                    for (int e = 1; e < P.K; ++e)
+                                        if (better(wv, wi, lv[e], li[e])) { wv = lv[e]; wi = li[e]; wp = e; }
+                                    thr_v = wv; thr_i = wi; thr_pos = wp;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+        }
+        if (row_ok) {
+            if (MODE == MODE_LSE) {
+                P.part_m[(size_t)row * P.n_splits + split] = m_run;
+                P.part_l[(size_t)row * P.n_splits + split] = l_run;
+            } else {
+                float* ov = P.cand_val + ((size_t)row * P.n_splits + split) * P.K;
+                int32_t* oi = P.cand_idx + ((size_t)row * P.n_splits + split) * P.K;
+                for (int e = 0; e < P.K; ++e) { ov[e] = lv[e]; oi[e] = li[e]; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// lse[b] = log sum_s l_s * exp(m_s - M) + M over the item splits
+__global__ void lse_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, int B, int n_splits,
+                                 float* __restrict__ lse) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float M = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) M = fmaxf(M, part_m[(size_t)b * n_splits + s]);
+    float l = 0.f;
+    for (int s = 0; s < n_splits; ++s) l += part_l[(size_t)b * n_splits + s] * expf(part_m[(size_t)b * n_splits + s] - M);
+    lse[b] = M + logf(l);
+}
+
+// fp32 [rows, cols] (leading dim ld_src) -> bf16 [rows, ld_dst] with zero padding of columns cols..ld_dst
+__global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, __nv_bfloat16* __restrict__ dst,
+                                 int ld_dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * ld_dst) return;
+    const int r = (int)(i / ld_dst), c = (int)(i - (int64_t)r * ld_dst);
+    dst[i] = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
+}
+
+// ---- host: TMA descriptors ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle, OOB -> 0
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return hvae_fail("cuTensorMapEncodeTiled is not available from the driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) return hvae_fail("TMA operand must be 16-byte aligned with ld %% 8 == 0 (ld=%d)", ld);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return hvae_fail("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return 0;
+}
+
+static int pick_splits(int m_tiles, int n_tiles) {
+    // one CTA per (user tile, item split); aim at ~2 waves of 148 SMs without leaving CTAs with < 1 tile
+    int want = (2 * kNumSMs) / m_tiles;
+    int splits = max(1, min(n_tiles, want));
+    const int tps = (n_tiles + splits - 1) / splits;
+    return (n_tiles + tps - 1) / tps;
+}
+
+constexpr size_t kStatsSmem = STAGES * STAGE_BYTES + 256 + BM * MAXK_TC * 8 + 1024;
+
+}  // namespace tc
+}  // namespace hvae
+
+using namespace hvae;
+using namespace hvae::tc;
+
+extern "C" {
+
+int hvae_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, void* stream) {
+    if (rows == 0) return 0;
+    const int64_t total = (int64_t)rows * ld_dst;
+    cast_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld_src, (__nv_bfloat16*)dst, ld_dst);
+    HVAE_LAUNCH_CHECK("cast_bf16");
+    return 0;
+}
+
+size_t hvae_tc_n_splits(int B, int N) { return (size_t)pick_splits(ceil_div(B, BM), ceil_div(N, BN)); }
+
+// workspace: 2 * B * n_splits floats
+int hvae_tc_score_lse(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* lse, float* workspace, void* stream) {
+    if (B == 0) return 0;
+    HVAE_REQUIRE(N > 0 && d > 0, "tc_score_lse: empty catalogue");
+    CUtensorMap tmU, tmE;
+    if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
+    if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, BN)) return rc;
+    const int m_tiles = ceil_div(B, BM), n_tiles = ceil_div(N, BN);
+    StatsParams P{};
+    P.B = B; P.N = N; P.d = d;
+    P.n_splits = pick_splits(m_tiles, n_tiles);
+    P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
+    P.part_m = workspace;
+    P.part_l = workspace + (size_t)B * P.n_splits;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        attr_set = true;
+    }
+    score_stats_kernel<MODE_LSE><<<dim3(m_tiles, P.n_splits), 192, kStatsSmem, (cudaStream_t)stream>>>(tmU, tmE, P);
+    HVAE_LAUNCH_CHECK("tc_score_lse");
+    lse_merge_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(P.part_m, P.part_l, B, P.n_splits, lse);
+    HVAE_LAUNCH_CHECK("tc_score_lse merge");
+    return 0;
+}
+
+// Top-K over the N items of E (global ids item_offset..item_offset+N).  cand_val / cand_idx: [B, n_splits*K] scratch;
+// the caller reduces them with hvae_topk_merge.  K <= 32.
+int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, int N, int d, int item_offset, const int64_t* indptr,
+                       const int32_t* indices, const int32_t* rows, int K, float* cand_val, int32_t* cand_idx, void* stream) {
+    if (B == 0) return 0;
+    HVAE_REQUIRE(K >= 1 && K <= MAXK_TC, "tc_score_topk: K=%d outside [1,%d]", K, MAXK_TC);
+    CUtensorMap tmU, tmE;
+    if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
+    if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, BN)) return rc;
+    const int m_tiles = ceil_div(B, BM), n_tiles = ceil_div(N, BN);
+    StatsParams P{};
+    P.B = B; P.N = N; P.d = d; P.K = K; P.item_offset = item_offset;
+    P.n_splits = pick_splits(m_tiles, n_tiles);
+    P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
+    P.cand_val = cand_val; P.cand_idx = cand_idx;
+    P.indptr = indptr; P.indices = indices; P.rows = rows;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        attr_set = true;
+    }
+    score_stats_kernel<MODE_TOPK><<<dim3(m_tiles, P.n_splits), 192, kStatsSmem, (cudaStream_t)stream>>>(tmU, tmE, P);
+    HVAE_LAUNCH_CHECK("tc_score_topk");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+"""GPU: the tcgen05 scoring kernels (bf16 mode) against plain torch on the same bf16-rounded operands.
+The kernels accumulate in fp32, so the only difference from `U.float() @ E.float().T` is summation order."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _r8(n):
+    return (n + 7) // 8 * 8
+
+
+def _operands(B, N, d, dev, seed=0, scale=3.0):
+    g = torch.Generator().manual_seed(seed)
+    U = (torch.randn(B, d, generator=g) * scale / d ** 0.5 * 4).to(dev)
+    E = torch.nn.functional.normalize(torch.randn(N, d, generator=g), dim=1).to(dev)
+    return U, E
+
+
+def _cast(lib, x, dev):
+    rows, cols = x.shape
+    ld = _r8(cols)
+    out = torch.empty(rows, ld, dtype=torch.bfloat16, device=dev)
+    lib.cast_bf16(x.data_ptr(), rows, cols, cols, out.data_ptr(), ld, torch.cuda.current_stream().cuda_stream)
+    return out, ld
+
+
+SHAPES = [(512, 12101, 384), (128, 256, 64), (77, 1000, 64), (300, 5000, 768), (130, 890, 384), (64, 300, 24), (1, 513, 200)]
+
+
+@pytest.mark.parametrize("B,N,d", SHAPES)
+def test_tc_lse_matches_torch(dev, B, N, d):
+    from hvae_b200 import _cabi
+    lib = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    U, E = _operands(B, N, d, dev)
+    Ub, ldu = _cast(lib, U.contiguous(), dev)
+    Eb, lde = _cast(lib, E.contiguous(), dev)
+    assert torch.equal(Ub[:, :d], U.to(torch.bfloat16)) and torch.all(Ub[:, d:] == 0)
+    ns = int(lib.tc_n_splits(B, N))
+    ws = torch.empty(2 * B * ns, device=dev)
+    lse = torch.empty(B, device=dev)
+    lib.tc_score_lse(Ub.data_ptr(), ldu, B, Eb.data_ptr(), lde, N, d, lse.data_ptr(), ws.data_ptr(), st)
+    ref = torch.logsumexp(Ub[:, :d].float().double() @ Eb[:, :d].float().double().t(), dim=1)
+    np.testing.assert_allclose(lse.cpu().numpy(), ref.cpu().numpy(), rtol=2e-6, atol=2e-5)
+
+
+@pytest.mark.parametrize("B,N,d,K", [(512, 12101, 384, 20), (77, 1000, 64, 10), (300, 5000, 768, 32), (130, 890, 384, 5), (3, 40, 24, 20)])
+def test_tc_topk_matches_torch(dev, B, N, d, K):
+    from hvae_b200 import _cabi
+    from hvae_b200.synth import make_interactions
+    lib = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    U, E = _operands(B, N, d, dev, seed=1)
+    Ub, ldu = _cast(lib, U.contiguous(), dev)
+    Eb, lde = _cast(lib, E.contiguous(), dev)
+    data = make_interactions(B, N, 3)
+    indptr = torch.from_numpy(data.indptr).to(dev)
+    indices = torch.from_numpy(data.indices).to(dev)
+    S = (Ub[:, :d].float() @ Eb[:, :d].float().t())
+    Sm = S.clone()
+    rr = torch.from_numpy(np.repeat(np.arange(B), np.diff(data.indptr))).to(dev)
+    Sm[rr, indices.long()] = -float("inf")
+    for (lo, hi) in [(0, N), (N // 3, N - 7)]:
+        n_it = hi - lo
+        ns = int(lib.tc_n_splits(B, n_it))
+        cv = torch.empty(B, ns * K, device=dev)
+        ci = torch.empty(B, ns * K, dtype=torch.int32, device=dev)
+        e_ptr = Eb.data_ptr() + 2 * lo * lde
+        lib.tc_score_topk(Ub.data_ptr(), ldu, B, e_ptr, lde, n_it, d, lo, indptr.data_ptr(), indices.data_ptr(), None, K,
+                          cv.data_ptr(), ci.data_ptr(), st)
+        ov = torch.empty(B, K, device=dev)
+        oi = torch.empty(B, K, dtype=torch.int32, device=dev)
+        lib.topk_merge(cv.data_ptr(), ci.data_ptr(), B, ns * K, K, ov.data_ptr(), oi.data_ptr(), st)
+        kk = min(K, n_it)
+        rv, ri = torch.topk(Sm[:, lo:hi], kk, dim=1)
+        got_v, got_i = ov.cpu().numpy(), oi.cpu().numpy()
+        ref_v = rv.cpu().numpy()
+        finite = np.isfinite(ref_v)
+        np.testing.assert_allclose(got_v[:, :kk][finite], ref_v[finite], rtol=1e-5, atol=1e-5)
+        # the returned ids carry the scores they claim, are unseen, and are inside the shard
+        Sm_c = Sm.cpu().numpy()
+        for b in range(B):
+            ids = got_i[b, :kk][finite[b]]
+            assert len(set(ids.tolist())) == len(ids)
+            assert np.all((ids >= lo) & (ids < hi))
+            np.testing.assert_allclose(Sm_c[b, ids], got_v[b, :kk][finite[b]], rtol=1e-5, atol=1e-5)
