@@ -102,8 +102,10 @@ int hvae_row_softmax_scale(float* S, int64_t lds, int rows, int N, const float* 
 int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
                          const void* U, int ldu, const void* E, int lde, int d, int is_bf16, float* dot, float* xsum,
                          void* stream);
+/* dU = s_b * sum_p O[p] - (1/Bg) * sum_j x_bj E_idx_j;  O: n_parts partial sums [n_parts][B][ldo];
+ * s_b = oscale ? oscale[b]/Bg : 1 (oscale = row sums |x|_b when O holds the plain softmax-weighted sums). */
 int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
-                     const float* O, int ldo, const float* oscale, const void* E, int lde, int d, int is_bf16,
+                     const float* O, int ldo, int n_parts, const float* oscale, const void* E, int lde, int d, int is_bf16,
                      const float* inv_bg, float* dU, int lddu, void* stream);
 int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, const int64_t* indptr,
                    const int32_t* indices, const int32_t* rows, int exclude_seen, int K, float* out_val,
@@ -130,6 +132,13 @@ int hvae_tc_score_lse(const void* U, int ldu, int B, const void* E, int lde, int
 int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, int N, int d, int item_offset,
                        const int64_t* indptr, const int32_t* indices, const int32_t* rows, int K, float* cand_val,
                        int32_t* cand_idx, void* stream);
+
+/* Backward through the scores: O[b,:] = sum_i softmax(S_b)_i E_i with S recomputed on the tensor cores
+ * (autograd of model.py:198,281; E is a frozen buffer, no dE).  lse from hvae_tc_score_lse.
+ * Opart: [hvae_tc_grad_splits(B,N,d)][B][ldo] partial sums over item splits. */
+size_t hvae_tc_grad_splits(int B, int N, int d);
+int hvae_tc_score_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, float* Opart,
+                       int ldo, void* stream);
 
 /* ---- optimiser (train.py:63,88-92; model.py:312-323) --------------------------------------------------- */
 int hvae_step_begin(hvae_step_state* state, double lr, double beta1, double beta2, double kl_beta_min, double kl_beta_max,

@@ -76,24 +76,28 @@ __global__ void __launch_bounds__(256) sparse_dot_xsum_kernel(const int64_t* __r
     if (lane == 0) { dot[b] = acc; xsum[b] = xs; }
 }
 
-// dU[b,:] = s_b * O[b,:] - inv_bg * sum_j x_bj E[idx_j,:];  s_b = oscale ? oscale[b] : 1
+// dU[b,:] = s_b * sum_p O[p][b,:] - inv_bg * sum_j x_bj E[idx_j,:];  s_b = oscale ? oscale[b] * inv_bg : 1
+// (O may come as n_parts partial sums over item splits, [n_parts][B][ldo], added in a fixed order.)
 template <typename T>
 __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                           const float* __restrict__ values, const int32_t* __restrict__ rows, int B,
-                                                          const float* __restrict__ O, int ldo, const float* __restrict__ oscale,
-                                                          const T* __restrict__ E, int lde, int d, const float* __restrict__ inv_bg,
-                                                          float* __restrict__ dU, int lddu) {
+                                                          const float* __restrict__ O, int ldo, int n_parts,
+                                                          const float* __restrict__ oscale, const T* __restrict__ E, int lde, int d,
+                                                          const float* __restrict__ inv_bg, float* __restrict__ dU, int lddu) {
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     const int u = rows ? rows[b] : b;
-    const float s = oscale ? oscale[b] : 1.0f, ib = *inv_bg;
+    const float ib = *inv_bg, s = oscale ? oscale[b] * ib : 1.0f;
+    const size_t pstride = (size_t)B * ldo;
     const int64_t js = indptr[u], je = indptr[u + 1];
     for (int c = lane; c < lddu; c += 32) {
         float g = 0.f;
         if (c < d) {
             float a = 0.f;
             for (int64_t j = js; j < je; ++j) a = fmaf(values ? values[j] : 1.0f, to_f(E[(size_t)indices[j] * lde + c]), a);
-            g = s * O[(size_t)b * ldo + c] - ib * a;
+            float o = 0.f;
+            for (int pp = 0; pp < n_parts; ++pp) o += O[pp * pstride + (size_t)b * ldo + c];
+            g = s * o - ib * a;
         }
         dU[(size_t)b * lddu + c] = g;
     }
@@ -300,14 +304,14 @@ int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const fl
 }
 
 int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B, const float* O,
-                     int ldo, const float* oscale, const void* E, int lde, int d, int is_bf16, const float* inv_bg, float* dU,
-                     int lddu, void* stream) {
+                     int ldo, int n_parts, const float* oscale, const void* E, int lde, int d, int is_bf16, const float* inv_bg,
+                     float* dU, int lddu, void* stream) {
     if (B == 0) return 0;
     if (is_bf16)
         du_finalize_kernel<__nv_bfloat16><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
-            indptr, indices, values, rows, B, O, ldo, oscale, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
+            indptr, indices, values, rows, B, O, ldo, n_parts, oscale, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
     else
-        du_finalize_kernel<float><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, O, ldo, oscale,
+        du_finalize_kernel<float><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
                                                                                    (const float*)E, lde, d, inv_bg, dU, lddu);
     HVAE_LAUNCH_CHECK("du_finalize");
     return 0;

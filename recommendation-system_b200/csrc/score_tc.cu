@@ -258,6 +258,218 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int co
     dst[i] = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Backward of the multinomial NLL through the scores: O[b,:] = sum_i softmax(S_b)_i * E_i, with S recomputed tile by
+// tile (never stored) and the softmax taken against the exact lse of the forward kernel.  Two chained GEMMs per
+// 128-item tile:  G1: S = U E_t^T (K = d, accumulators in TMEM)  ->  registers: P = exp(S - lse_b) -> bf16 -> smem
+// (128B-swizzled, K-major)  ->  G2: O += P E_t (K = 128 items; B operand = the same E rows read MN-major).
+// One CTA = (128 users, <=384 columns of O, a range of item tiles).  No gradient for E (frozen buffer).
+constexpr int G_BN = 128;                     // items per tile
+constexpr int G_STAGES = 4, G_SLOT = 32768;   // ring slot: U [128x64] + E [128x64] for G1, or E [64 x <=256] for G2
+constexpr int G_DCHUNK = 384;                 // O columns per CTA (TMEM: 384 O + 128 S = 512)
+constexpr int G_PBYTES = 32768;               // P tile [128 users x 128 items] bf16 = two [128x64] swizzle atoms columns
+
+struct GradParams {
+    int B, N, d;
+    int tiles_per_split, n_splits;
+    const float* lse;     // [B]
+    float* Opart;         // [n_splits][B][ldo]
+    int ldo;
+};
+
+struct __align__(8) GradBarriers {
+    uint64_t full[G_STAGES], empty[G_STAGES], s_full, s_free, p_full[2], p_free[2], o_full;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constant__ CUtensorMap tmU,
+                                                            const __grid_constant__ CUtensorMap tmE, GradParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* pbuf = smem + G_STAGES * G_SLOT;                         // 2 x 32 KB
+    GradBarriers* bars = reinterpret_cast<GradBarriers*>(pbuf + 2 * G_PBYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, chunk = blockIdx.y, split = blockIdx.z;
+    const int n_tiles_total = (P.N + G_BN - 1) / G_BN;
+    const int t0 = split * P.tiles_per_split, t1 = min(n_tiles_total, t0 + P.tiles_per_split);
+    const int T = t1 - t0;
+    const int KB = (P.d + BK - 1) / BK;
+    const int dpad = KB * BK;
+    const int dc0 = chunk * G_DCHUNK;                  // first O column of this CTA
+    const int DC = min(G_DCHUNK, dpad - dc0);          // multiple of 64
+    const int NG = (DC + 255) / 256;                   // column groups of <= 256 per G2 MMA
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmU);
+        tma_prefetch_desc(&tmE);
+        for (int s = 0; s < G_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        mbar_init(&bars->s_full, 1); mbar_init(&bars->s_free, 4); mbar_init(&bars->o_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars->p_full[a], 4); mbar_init(&bars->p_free[a], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            auto acquire = [&](uint32_t bytes) {
+                const int s = it % G_STAGES;
+                mbar_wait(&bars->empty[s], ((it / G_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&bars->full[s], bytes);
+                ++it;
+                return s;
+            };
+            for (int ti = 0; ti <= T; ++ti) {
+                if (ti < T) {          // G1 operands of tile ti
+                    const int item0 = (t0 + ti) * G_BN;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const int s = acquire(G_SLOT);
+                        uint8_t* slot = smem + s * G_SLOT;
+                        tma_load_2d(slot, &tmU, kb * BK, m_tile * BM, &bars->full[s]);
+                        tma_load_2d(slot + 16384, &tmE, kb * BK, item0, &bars->full[s]);
+                        tma_load_2d(slot + 16384 + 8192, &tmE, kb * BK, item0 + 64, &bars->full[s]);
+                    }
+                }
+                if (ti >= 1) {         // G2 operands of tile ti-1: E rows as [64 items x (<=256 columns)] blocks
+                    const int item0 = (t0 + ti - 1) * G_BN;
+                    for (int ih = 0; ih < 2; ++ih)
+                        for (int g = 0; g < NG; ++g) {
+                            const int nb = min(4, (DC - g * 256) / 64);
+                            const int s = acquire(nb * 8192);
+                            uint8_t* slot = smem + s * G_SLOT;
+                            for (int j = 0; j < nb; ++j)
+                                tma_load_2d(slot + j * 8192, &tmE, dc0 + g * 256 + j * 64, item0 + ih * 64, &bars->full[s]);
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = make_idesc(BM, G_BN, 0, 0);
+            int it = 0;
+            for (int ti = 0; ti <= T; ++ti) {
+                if (ti < T) {          // G1(ti): S = U E_t^T
+                    mbar_wait(&bars->s_free, (ti & 1) ^ 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        const int s = it % G_STAGES;
+                        mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(smem + s * G_SLOT), b0 = a0 + 16384;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_ss(tmem_S, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc1, (kb | k) != 0);
+                        umma_commit(&bars->empty[s]);
+                    }
+                    umma_commit(&bars->s_full);
+                }
+                if (ti >= 1) {         // G2(ti-1): O += P E_t
+                    const int tj = ti - 1, pb = tj & 1;
+                    mbar_wait(&bars->p_full[pb], (tj >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t p0 = smem_u32(pbuf + pb * G_PBYTES);
+                    for (int ih = 0; ih < 2; ++ih)
+                        for (int g = 0; g < NG; ++g, ++it) {
+                            const int ncols = min(256, DC - g * 256);
+                            const uint32_t idesc2 = make_idesc(BM, ncols, 0, 1);
+                            const int s = it % G_STAGES;
+                            mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t b0 = smem_u32(smem + s * G_SLOT);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)      // K = 16 items per MMA
+                                umma_ss(tmem_O + g * 256, make_desc(p0 + ih * 16384 + kk * 32, 16, 1024),
+                                        make_desc(b0 + kk * 2048, 8192, 1024), idesc2, (tj | ih | kk) != 0);
+                            umma_commit(&bars->empty[s]);
+                        }
+                    umma_commit(&bars->p_free[pb]);
+                }
+            }
+            umma_commit(&bars->o_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int r_local = q * 32 + lane;
+        const int row = m_tile * BM + r_local;
+        const bool row_ok = row < P.B;
+        const float lse2 = row_ok ? P.lse[row] * kLog2e : 0.f;
+        const uint32_t lane_base = uint32_t(q * 32) << 16;
+        for (int ti = 0; ti < T; ++ti) {
+            const int pb = ti & 1;
+            mbar_wait(&bars->s_full, ti & 1);
+            tc_fence_after();
+            float v[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(tmem_S + lane_base + c * 32, v[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->s_free);
+            mbar_wait(&bars->p_free[pb], ((ti >> 1) & 1) ^ 1);
+            uint8_t* prow = pbuf + pb * G_PBYTES + r_local * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {         // 8 items -> one 16-byte chunk
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float p0 = exp2f(fmaf(v[c][j8 * 8 + 2 * e], kLog2e, -lse2));
+                        const float p1 = exp2f(fmaf(v[c][j8 * 8 + 2 * e + 1], kLog2e, -lse2));
+                        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+                        w[e] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    const int item = c * 32 + j8 * 8;            // local item index 0..127
+                    const int atom = item >> 6, chunk16 = (item & 63) >> 3;
+                    uint8_t* dst = prow + atom * 16384 + ((chunk16 ^ (r_local & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->p_full[pb]);
+        }
+        // ---- O (TMEM) -> global partial ---------------------------------------------------------------------
+        mbar_wait(&bars->o_full, 0);
+        tc_fence_after();
+        float* orow = P.Opart + ((size_t)split * P.B + row) * P.ldo + dc0;
+        for (int c = 0; c < DC / 32; ++c) {
+            float v[32];
+            tmem_ld32(tmem_O + lane_base + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (dc0 + c * 32 + j < P.ldo)
+                        *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+constexpr size_t kGradSmem = G_STAGES * G_SLOT + 2 * G_PBYTES + 256 + 1024;
+
+static int pick_grad_splits(int m_tiles, int n_chunks, int n_tiles) {
+    const int want = (2 * kNumSMs) / (m_tiles * n_chunks);
+    const int splits = max(1, min(n_tiles, want));
+    const int tps = (n_tiles + splits - 1) / splits;
+    return (n_tiles + tps - 1) / tps;
+}
+
 // ---- host: TMA descriptors ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -368,6 +580,35 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
     }
     score_stats_kernel<MODE_TOPK><<<dim3(m_tiles, P.n_splits), 192, kStatsSmem, (cudaStream_t)stream>>>(tmU, tmE, P);
     HVAE_LAUNCH_CHECK("tc_score_topk");
+    return 0;
+}
+
+
+size_t hvae_tc_grad_splits(int B, int N, int d) {
+    return (size_t)pick_grad_splits(ceil_div(B, BM), ceil_div(round_up(d, BK), G_DCHUNK), ceil_div(N, G_BN));
+}
+
+// Opart: [hvae_tc_grad_splits(B,N,d)][B][ldo] floats, ldo % 4 == 0, ldo >= d; every partial is fully written for
+// columns < min(ldo, round_up(d,64)).  O = sum of the partials (hvae_du_finalize does it).
+int hvae_tc_score_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, float* Opart, int ldo,
+                       void* stream) {
+    if (B == 0) return 0;
+    HVAE_REQUIRE(ldo % 4 == 0 && ldo >= d, "tc_score_grad: bad ldo=%d for d=%d", ldo, d);
+    CUtensorMap tmU, tmE;
+    if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
+    if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, 64)) return rc;
+    const int m_tiles = ceil_div(B, BM), n_chunks = ceil_div(round_up(d, BK), G_DCHUNK), n_tiles = ceil_div(N, G_BN);
+    GradParams P{};
+    P.B = B; P.N = N; P.d = d; P.lse = lse; P.Opart = Opart; P.ldo = ldo;
+    P.n_splits = pick_grad_splits(m_tiles, n_chunks, n_tiles);
+    P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
+    static bool attr_set = false;
+    if (!attr_set) {
+        HVAE_CUDA(cudaFuncSetAttribute(score_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
+        attr_set = true;
+    }
+    score_grad_kernel<<<dim3(m_tiles, n_chunks, P.n_splits), 192, kGradSmem, (cudaStream_t)stream>>>(tmU, tmE, P);
+    HVAE_LAUNCH_CHECK("tc_score_grad");
     return 0;
 }
 

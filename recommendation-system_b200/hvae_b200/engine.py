@@ -21,6 +21,10 @@ def r4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+def r8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
 @dataclass
 class Slot:
     off: int      # offset in floats from the arena start
@@ -240,9 +244,12 @@ class Engine:
 
     @property
     def E_bf16(self):
-        """bf16 copy of the frozen item matrix for the tensor-core scoring kernels (half the HBM bytes)."""
+        """bf16 copy [N, r8(d)] (zero-padded columns) of the frozen item matrix for the tensor-core scoring
+        kernels: half the HBM bytes, rows 16-byte aligned for TMA."""
         if self._E_bf16 is None:
-            self._E_bf16 = self.E.to(torch.bfloat16).contiguous()
+            N, d = self.lay.N, self.lay.d
+            self._E_bf16 = torch.empty(N, r8(d), dtype=torch.bfloat16, device=self.dev)
+            self.lib.cast_bf16(p(self.E), N, d, d, p(self._E_bf16), r8(d), self.stream)
         return self._E_bf16
 
     def invalidate_embeddings(self):
@@ -406,9 +413,10 @@ class Engine:
         else:
             dU = ws.get("dU", (B, ldd))
             is_bf16 = 0 if self.precision == "fp32" else 1
-            Eg = self.E if not is_bf16 else self.E_bf16
-            lib.du_finalize(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(O), ldd, p(oscale), p(Eg), d, d,
-                            is_bf16, self.state_ptr("inv_bg"), p(dU), ldd, st)
+            Eg, lde = (self.E, d) if not is_bf16 else (self.E_bf16, r8(d))
+            n_parts = O.shape[0] if O.dim() == 3 else 1
+            lib.du_finalize(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(O), ldd, n_parts, p(oscale), p(Eg),
+                            lde, d, is_bf16, self.state_ptr("inv_bg"), p(dU), ldd, st)
         if lay.identity_proj:
             dz = dU
         else:

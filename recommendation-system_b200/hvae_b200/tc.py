@@ -1,0 +1,68 @@
+"""bf16 tensor-core mode of the scoring stage: sequencing of the tcgen05 kernels of csrc/score_tc.cu.
+
+The user vectors u = projection(z) are rounded to bf16, E is held as a bf16 copy; products accumulate in fp32 in
+TMEM.  The [B, N] score matrix is never written: the forward kernel's epilogue folds it into per-user
+log-sum-exp, the backward kernel recomputes it tile by tile and feeds softmax(S) straight into the second GEMM
+(src/ml/model.py:198,281 and their autograd), the evaluation kernel folds it into a per-user top-K
+(src/ml/evaluate.py:125-147).
+"""
+from __future__ import annotations
+
+import torch
+
+from ._cabi import p
+from .engine import r4, r8
+
+MAX_K_TC = 32
+
+
+def user_vectors_bf16(eng, u, B):
+    d = eng.lay.d
+    ub = eng.ws.get("u_bf16", (B, r8(d)), torch.bfloat16)
+    eng.lib.cast_bf16(p(u), B, d, r4(d), p(ub), r8(d), eng.stream)
+    return ub
+
+
+def score_loss_bf16(eng, batch, u, want_grad):
+    """-> (lse [B], dot [B], xsum [B], O partial sums [splits, B, ld] or None, per-row scale of O)."""
+    lay, ws, lib, st = eng.lay, eng.ws, eng.lib, eng.stream
+    B, N, d = batch.B, lay.N, lay.d
+    ldd, ld8 = r4(d), r8(d)
+    csr = batch.csr
+    Eb = eng.E_bf16
+    ub = user_vectors_bf16(eng, u, B)
+    lse, dot, xsum = ws.get("lse", (B,)), ws.get("dot", (B,)), ws.get("xsum", (B,))
+    lib.sparse_dot_xsum(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(ub), ld8, p(Eb), ld8, d, 1,
+                        p(dot), p(xsum), st)
+    ns = int(lib.tc_n_splits(B, N))
+    wsl = ws.get("tc_lse_ws", (2 * B * ns,))
+    with eng.span("score_fwd"):
+        lib.tc_score_lse(p(ub), ld8, B, p(Eb), ld8, N, d, p(lse), p(wsl), st)
+    O = None
+    if want_grad:
+        gs = int(lib.tc_grad_splits(B, N, d))
+        O = ws.get("tc_O", (gs, B, ldd))
+        with eng.span("score_bwd"):
+            lib.tc_score_grad(p(ub), ld8, B, p(Eb), ld8, N, d, p(lse), p(O), ldd, st)
+    return lse, dot, xsum, O, xsum
+
+
+def topk_bf16(eng, batch, u, K, exclude_seen, item_lo, item_hi, out_val, out_idx) -> bool:
+    """Fused score + seen-mask + top-K over items [item_lo, item_hi).  False if K is beyond the fused kernel."""
+    if K > MAX_K_TC:
+        return False
+    lay, ws, lib, st = eng.lay, eng.ws, eng.lib, eng.stream
+    B, d = batch.B, lay.d
+    ld8 = r8(d)
+    n_it = item_hi - item_lo
+    Eb = eng.E_bf16
+    ub = user_vectors_bf16(eng, u, B)
+    ns = int(lib.tc_n_splits(B, n_it))
+    cv = ws.get("tc_cand_v", (B, ns * K))
+    ci = ws.get("tc_cand_i", (B, ns * K), torch.int32)
+    csr = batch.csr
+    with eng.span("score_topk"):
+        lib.tc_score_topk(p(ub), ld8, B, Eb.data_ptr() + 2 * item_lo * ld8, ld8, n_it, d, item_lo,
+                          p(csr.indptr) if exclude_seen else None, p(csr.indices), p(batch.rows), K, p(cv), p(ci), st)
+    lib.topk_merge(p(cv), p(ci), B, ns * K, K, p(out_val), p(out_idx), st)
+    return True

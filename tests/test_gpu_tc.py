@@ -92,3 +92,32 @@ def test_tc_topk_matches_torch(dev, B, N, d, K):
             assert len(set(ids.tolist())) == len(ids)
             assert np.all((ids >= lo) & (ids < hi))
             np.testing.assert_allclose(Sm_c[b, ids], got_v[b, :kk][finite[b]], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,N,d", [(512, 12101, 384), (128, 256, 64), (77, 1000, 64), (300, 5000, 768), (130, 890, 384), (64, 300, 24),
+                                   (1, 513, 200), (256, 3000, 448)])
+def test_tc_grad_matches_torch(dev, B, N, d):
+    """O = softmax(S) E with S recomputed on the tensor cores and P rounded to bf16 before the second GEMM."""
+    from hvae_b200 import _cabi
+    lib = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    U, E = _operands(B, N, d, dev, seed=2)
+    Ub, ldu = _cast(lib, U.contiguous(), dev)
+    Eb, lde = _cast(lib, E.contiguous(), dev)
+    ns = int(lib.tc_n_splits(B, N))
+    ws = torch.empty(2 * B * ns, device=dev)
+    lse = torch.empty(B, device=dev)
+    lib.tc_score_lse(Ub.data_ptr(), ldu, B, Eb.data_ptr(), lde, N, d, lse.data_ptr(), ws.data_ptr(), st)
+    gs = int(lib.tc_grad_splits(B, N, d))
+    ldo = (d + 3) // 4 * 4
+    Op = torch.full((gs, B, ldo), float("nan"), device=dev)
+    lib.tc_score_grad(Ub.data_ptr(), ldu, B, Eb.data_ptr(), lde, N, d, lse.data_ptr(), Op.data_ptr(), ldo, st)
+    O = Op.sum(0)[:, :d].double().cpu()
+    S = Ub[:, :d].float().double() @ Eb[:, :d].float().double().t()
+    Pm = torch.softmax(S, dim=1)
+    ref = (Pm @ Eb[:, :d].float().double()).cpu()
+    ref_b = (Pm.float().to(torch.bfloat16).double() @ Eb[:, :d].float().double()).cpu()
+    scale = float(ref.abs().max())
+    assert torch.isfinite(O).all()
+    assert float((O - ref_b).abs().max()) < 2e-3 * scale + 1e-6      # same rounding point: only exp ulps / order differ
+    assert float((O - ref).abs().max()) < 1e-2 * scale + 1e-6        # against exact softmax: bf16 rounding of P
