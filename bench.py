@@ -218,12 +218,12 @@ def main():
     lens = np.diff(data.indptr)
     n_batches = U // Bg if U >= Bg else 1
 
+    cap_local = max(int(lens[order[i * Bg + rank * B:i * Bg + (rank + 1) * B]].sum()) for i in range(n_batches))
+    cap_global = max(int(lens[order[i * Bg:(i + 1) * Bg]].sum()) for i in range(n_batches))
+
     def batch_at(s):
         g0 = (s % n_batches) * Bg
-        rows_h = order[g0 + rank * B:g0 + (rank + 1) * B]
-        cap_g = int(lens[order[g0:g0 + Bg]].sum())
-        return Batch(csr, order_dev[g0 + rank * B:g0 + (rank + 1) * B], B, max(1, int(lens[rows_h].sum())), b_global=Bg,
-                     nnz_cap_global=cap_g)
+        return Batch(csr, order_dev[g0 + rank * B:g0 + (rank + 1) * B], B, max(1, cap_local), b_global=Bg, nnz_cap_global=cap_global)
 
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     model.train()
@@ -394,7 +394,7 @@ def main():
             "config": workload_config(args.workload, c, world, args.precision),
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
             "value_hot_l2": K * Bg / (ms_hot * 1e-3), "ms_per_step_hot_l2": ms_hot / K,
-            "kernels": kernels, "spans_ms": span_avg, "eval": ev_out, "cuda_graph": bool(trainer.use_cuda_graph)}
+            "kernels": kernels, "spans_ms": span_avg, "eval": ev_out, "cuda_graph": bool(trainer.use_cuda_graph and world == 1)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

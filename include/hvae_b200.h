@@ -41,6 +41,8 @@ typedef struct hvae_step_state {
     float clip_coef;     /* min(1, max_norm / (||g|| + 1e-6)) */
     float grad_norm;     /* ||g||_2 before clipping */
     float norm2;         /* ||g||_2^2 */
+    uint32_t noise_lo;   /* 64-bit Philox counter base of the in-kernel dropout / eps noise, advanced per step */
+    uint32_t noise_hi;
 } hvae_step_state;
 
 const char* hvae_last_error(void);
@@ -141,15 +143,17 @@ int hvae_tc_score_grad(const void* U, int ldu, int B, const void* E, int lde, in
                        int ldo, void* stream);
 
 /* ---- optimiser (train.py:63,88-92; model.py:312-323) --------------------------------------------------- */
+/* advance != 0: a training step (Adam step count, annealing step and the noise counter (+= noise_stride) move on) */
 int hvae_step_begin(hvae_step_state* state, double lr, double beta1, double beta2, double kl_beta_min, double kl_beta_max,
-                    int anneal_steps, int b_global, int advance, void* stream);
+                    int anneal_steps, int b_global, int advance, uint32_t noise_stride, void* stream);
 int hvae_grad_norm_clip(const float* gdense, int64_t n_dense, const float* rownorm2, const int32_t* n_unique,
                         float max_norm, hvae_step_state* state, float* workspace, void* stream);
 int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_params, int64_t n_w1, int ld1,
                    const int32_t* slot_of_item, const float* gsparse, const float* gdense, const hvae_step_state* state,
                    float weight_decay, float beta1, float beta2, float eps, void* stream);
+/* Counter-based (Philox4x32-10) keep-masks / standard normals; counter = offset + state->noise (state may be NULL). */
 int hvae_fill_noise(uint8_t* mask, int64_t n_mask, float keep_prob, float* eps, int64_t n_eps, uint64_t seed,
-                    uint64_t offset, uint32_t stream_id, void* stream);
+                    uint64_t offset, uint32_t stream_id, const hvae_step_state* state, void* stream);
 
 #ifdef __cplusplus
 }

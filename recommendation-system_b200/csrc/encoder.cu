@@ -217,12 +217,28 @@ __global__ void __launch_bounds__(256) ln_act_bwd_kernel(const float* dact, cons
             reinterpret_cast<float4*>(dpre)[(size_t)row * ld4 + col4] = o;
         }
     }
-    float4* pg = reinterpret_cast<float4*>(partial) + (size_t)warp * 2 * ld4;
+    // block-level reduction in a fixed warp order (deterministic), one partial row [2][ld] per block
+    extern __shared__ float4 bred[];  // [2][ld4]
+    const int wib = threadIdx.x >> 5;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        if (wib == w) {
 #pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) {
-        const int col4 = lane + 32 * c;
-        if (col4 < ld4) { pg[col4] = ag[c]; pg[ld4 + col4] = ab[c]; }
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int col4 = lane + 32 * c;
+                if (col4 >= ld4) continue;
+                if (w == 0) { bred[col4] = ag[c]; bred[ld4 + col4] = ab[c]; }
+                else {
+                    float4 a = bred[col4], b = bred[ld4 + col4];
+                    a.x += ag[c].x; a.y += ag[c].y; a.z += ag[c].z; a.w += ag[c].w;
+                    b.x += ab[c].x; b.y += ab[c].y; b.z += ab[c].z; b.w += ab[c].w;
+                    bred[col4] = a; bred[ld4 + col4] = b;
+                }
+            }
+        }
+        __syncthreads();
     }
+    float4* pg = reinterpret_cast<float4*>(partial) + (size_t)blockIdx.x * 2 * ld4;
+    for (int i = threadIdx.x; i < 2 * ld4; i += blockDim.x) pg[i] = bred[i];
 }
 
 // out[chunk][c] = sum over rows r in [chunk*rpc, min(R,(chunk+1)*rpc)) of X[r][c]   (fixed order)
@@ -244,7 +260,11 @@ __global__ void colsum_chunk_kernel(const float* __restrict__ X, int ld, int R, 
 }
 
 // One CTA (4 warps) per touched item: grad row = sum over the item's (user, value) entries of
-// value * dH[user, :].  Entries were sorted stably by item, so the order -- hence the fp32 sum -- is fixed.
+// value * dH[user, :].  Entries were sorted stably by item, so the order -- hence the fp32 sum -- is fixed:
+// warp w sums entries w, w+4, ... in order, the four warp sums are combined as (0+1)+(2+3).
+// Entry ids are fetched 32 at a time (one per lane) and broadcast, every row is read as NCHUNK 16-byte
+// vectors per lane with two rows in flight.
+template <int NCHUNK>
 __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_unique,
                                                       const int32_t* __restrict__ sorted_eid, const int32_t* __restrict__ ent_user,
                                                       const float* __restrict__ ent_val, const float* __restrict__ dpre, int ld4,
@@ -254,27 +274,61 @@ __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict_
     if (slot >= *n_unique) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = seg_start[slot], e = seg_start[slot + 1];
-    const int nch = (ld4 + 31) / 32;
-    for (int c = 0; c < nch; ++c) {
-        const int col4 = lane + 32 * c;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col4 < ld4) {
-            for (int j = s + warp; j < e; j += 4) {
-                const int eid = sorted_eid[j];
-                const float v = ent_val[eid];
-                const float4 g = __ldg(reinterpret_cast<const float4*>(dpre) + (size_t)ent_user[eid] * ld4 + col4);
-                a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+    const float4* dp = reinterpret_cast<const float4*>(dpre);
+    float4 a[NCHUNK];
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) a[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = s + warp; base < e; base += 4 * 32) {
+        const int mine = base + 4 * lane;
+        int my_user = 0;
+        float my_val = 0.f;
+        if (mine < e) { const int eid = sorted_eid[mine]; my_user = ent_user[eid]; my_val = ent_val[eid]; }
+        const int cnt = min(32, (e - base + 3) / 4);
+        int t = 0;
+        for (; t + 2 <= cnt; t += 2) {
+            const int u0 = __shfl_sync(0xffffffffu, my_user, t), u1 = __shfl_sync(0xffffffffu, my_user, t + 1);
+            const float v0 = __shfl_sync(0xffffffffu, my_val, t), v1 = __shfl_sync(0xffffffffu, my_val, t + 1);
+            float4 g0[NCHUNK], g1[NCHUNK];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int col4 = lane + 32 * c;
+                if (col4 < ld4) { g0[c] = __ldg(dp + (size_t)u0 * ld4 + col4); g1[c] = __ldg(dp + (size_t)u1 * ld4 + col4); }
+                else { g0[c] = make_float4(0.f, 0.f, 0.f, 0.f); g1[c] = g0[c]; }
             }
-            red[warp * ld4 + col4] = a;
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                a[c].x = fmaf(v0, g0[c].x, a[c].x); a[c].y = fmaf(v0, g0[c].y, a[c].y);
+                a[c].z = fmaf(v0, g0[c].z, a[c].z); a[c].w = fmaf(v0, g0[c].w, a[c].w);
+                a[c].x = fmaf(v1, g1[c].x, a[c].x); a[c].y = fmaf(v1, g1[c].y, a[c].y);
+                a[c].z = fmaf(v1, g1[c].z, a[c].z); a[c].w = fmaf(v1, g1[c].w, a[c].w);
+            }
         }
+        if (t < cnt) {
+            const int u0 = __shfl_sync(0xffffffffu, my_user, t);
+            const float v0 = __shfl_sync(0xffffffffu, my_val, t);
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int col4 = lane + 32 * c;
+                if (col4 < ld4) {
+                    const float4 g = __ldg(dp + (size_t)u0 * ld4 + col4);
+                    a[c].x = fmaf(v0, g.x, a[c].x); a[c].y = fmaf(v0, g.y, a[c].y);
+                    a[c].z = fmaf(v0, g.z, a[c].z); a[c].w = fmaf(v0, g.w, a[c].w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        const int col4 = lane + 32 * c;
+        if (col4 < ld4) red[warp * ld4 + col4] = a[c];
     }
     __syncthreads();
     float n2 = 0.f;
     for (int col4 = threadIdx.x; col4 < ld4; col4 += 128) {
-        const float4 a = red[col4], b = red[ld4 + col4], c = red[2 * ld4 + col4], d = red[3 * ld4 + col4];
+        const float4 a0 = red[col4], b = red[ld4 + col4], c = red[2 * ld4 + col4], d = red[3 * ld4 + col4];
         float4 o;
-        o.x = (a.x + b.x) + (c.x + d.x); o.y = (a.y + b.y) + (c.y + d.y);
-        o.z = (a.z + b.z) + (c.z + d.z); o.w = (a.w + b.w) + (c.w + d.w);
+        o.x = (a0.x + b.x) + (c.x + d.x); o.y = (a0.y + b.y) + (c.y + d.y);
+        o.z = (a0.z + b.z) + (c.z + d.z); o.w = (a0.w + b.w) + (c.w + d.w);
         reinterpret_cast<float4*>(gs)[(size_t)slot * ld4 + col4] = o;
         n2 += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
     }
@@ -358,11 +412,13 @@ int hvae_ln_act_bwd(const float* dact, const float* pre, const float* mean, cons
     if (B == 0) return 0;
     const int nch = ceil_div(ld / 4, 32);
     const int blocks = ln_bwd_blocks(B);
-    DISPATCH_NCHUNK(nch, (ln_act_bwd_kernel<NC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    const size_t smem = (size_t)2 * ld * sizeof(float);
+    HVAE_REQUIRE(smem <= 48 * 1024, "ln_act_bwd: hidden width %d too large", ld);
+    DISPATCH_NCHUNK(nch, (ln_act_bwd_kernel<NC><<<blocks, 256, smem, (cudaStream_t)stream>>>(
                              dact, pre, mean, rstd, gamma, beta, mask, keep_scale, B, h, ld / 4, dpre, workspace)));
     HVAE_LAUNCH_CHECK("ln_act_bwd");
-    // partial rows are [2*ld] wide: first ld = d(gamma), next ld = d(beta)
-    const int R = blocks * 8;
+    // one partial row per block, [2*ld] wide: first ld = d(gamma), next ld = d(beta)
+    const int R = blocks;
     colsum_chunk_kernel<<<dim3(ceil_div(h, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace, 2 * ld, R, h, R, dgamma, h);
     colsum_chunk_kernel<<<dim3(ceil_div(h, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace + ld, 2 * ld, R, h, R, dbeta, h);
     HVAE_LAUNCH_CHECK("ln_act_bwd colsum");
@@ -372,7 +428,7 @@ int hvae_ln_act_bwd(const float* dact, const float* pre, const float* mean, cons
 // out[c] = sum_r X[r][c]; two fixed-order stages through `workspace` (>= 64*C floats)
 int hvae_colsum(const float* X, int ld, int R, int C, float* out, float* workspace, void* stream) {
     if (C == 0) return 0;
-    const int chunks = max(1, min(64, ceil_div(R, 64)));
+    const int chunks = max(1, min(64, ceil_div(R, 16)));
     const int rpc = ceil_div(max(R, 1), chunks);
     colsum_chunk_kernel<<<dim3(ceil_div(C, 128), chunks), 128, 0, (cudaStream_t)stream>>>(X, ld, R, C, rpc, workspace, C);
     colsum_chunk_kernel<<<dim3(ceil_div(C, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace, C, chunks, C, chunks, out, C);
@@ -386,8 +442,10 @@ int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_
     if (max_slots == 0) return 0;
     const size_t smem = (size_t)4 * ld * sizeof(float);
     HVAE_REQUIRE(smem <= 48 * 1024, "w1_grad: hidden width %d too large", ld);
-    w1_grad_kernel<<<max_slots, 128, smem, (cudaStream_t)stream>>>(seg_start, n_unique, sorted_eid, ent_user, ent_val, dpre,
-                                                                   ld / 4, gs, rownorm2);
+    const int h = ld;
+    const int nch = ceil_div(ld / 4, 32);
+    DISPATCH_NCHUNK(nch, (w1_grad_kernel<NC><<<max_slots, 128, smem, (cudaStream_t)stream>>>(seg_start, n_unique, sorted_eid, ent_user,
+                                                                                             ent_val, dpre, ld / 4, gs, rownorm2)));
     HVAE_LAUNCH_CHECK("w1_grad");
     return 0;
 }

@@ -9,7 +9,7 @@ namespace hvae {
 
 // All step-dependent scalars live on the device so that a captured CUDA graph can be replayed unchanged.
 __global__ void step_begin_kernel(hvae_step_state* st, double lr, double b1, double b2, double beta_min, double beta_max,
-                                  int anneal_steps, int b_global, int advance_adam) {
+                                  int anneal_steps, int b_global, int advance_adam, uint32_t noise_stride) {
     if (advance_adam) {
         const int step = ++st->adam_step;
         const double bc1 = 1.0 - pow(b1, (double)step);
@@ -22,6 +22,11 @@ __global__ void step_begin_kernel(hvae_step_state* st, double lr, double b1, dou
         const int cur = st->anneal_step;
         if (cur < anneal_steps) beta = beta_min + ((double)cur / (double)anneal_steps) * (beta_max - beta_min);
         if (advance_adam) st->anneal_step = cur + 1;
+    }
+    if (advance_adam) {
+        const uint64_t ctr = ((uint64_t)st->noise_hi << 32 | st->noise_lo) + noise_stride;
+        st->noise_lo = (uint32_t)ctr;
+        st->noise_hi = (uint32_t)(ctr >> 32);
     }
     st->beta_kl = (float)beta;
     st->inv_bg = 1.0f / (float)b_global;
@@ -116,9 +121,11 @@ __device__ __forceinline__ void philox(uint64_t seed, uint64_t ctr, uint32_t str
     out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
 
-__global__ void noise_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float keep, uint64_t seed, uint64_t offset, uint32_t sid) {
+__global__ void noise_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float keep, uint64_t seed, uint64_t offset, uint32_t sid,
+                                  const hvae_step_state* __restrict__ st) {
     const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 * 4 >= n) return;
+    if (st) offset += ((uint64_t)st->noise_hi << 32 | st->noise_lo);
     uint32_t r[4];
     philox(seed, offset + (uint64_t)i4, sid, r);
     for (int k = 0; k < 4; ++k) {
@@ -127,9 +134,11 @@ __global__ void noise_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float k
     }
 }
 
-__global__ void noise_normal_kernel(float* __restrict__ eps, int64_t n, uint64_t seed, uint64_t offset, uint32_t sid) {
+__global__ void noise_normal_kernel(float* __restrict__ eps, int64_t n, uint64_t seed, uint64_t offset, uint32_t sid,
+                                    const hvae_step_state* __restrict__ st) {
     const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 * 4 >= n) return;
+    if (st) offset += ((uint64_t)st->noise_hi << 32 | st->noise_lo);
     uint32_t r[4];
     philox(seed, offset + (uint64_t)i4, sid, r);
     for (int k = 0; k < 4; k += 2) {
@@ -151,9 +160,10 @@ using namespace hvae;
 extern "C" {
 
 int hvae_step_begin(hvae_step_state* state, double lr, double beta1, double beta2, double kl_beta_min, double kl_beta_max,
-                    int anneal_steps, int b_global, int advance, void* stream) {
+                    int anneal_steps, int b_global, int advance, uint32_t noise_stride, void* stream) {
     HVAE_REQUIRE(b_global > 0, "step_begin: global batch must be positive");
-    step_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2, kl_beta_min, kl_beta_max, anneal_steps, b_global, advance);
+    step_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2, kl_beta_min, kl_beta_max, anneal_steps, b_global, advance,
+                                                         noise_stride);
     HVAE_LAUNCH_CHECK("step_begin");
     return 0;
 }
@@ -182,11 +192,13 @@ int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_p
 }
 
 int hvae_fill_noise(uint8_t* mask, int64_t n_mask, float keep_prob, float* eps, int64_t n_eps, uint64_t seed, uint64_t offset,
-                    uint32_t stream_id, void* stream) {
+                    uint32_t stream_id, const hvae_step_state* state, void* stream) {
     if (mask && n_mask > 0)
-        noise_mask_kernel<<<(unsigned)((n_mask / 4 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(mask, n_mask, keep_prob, seed, offset, stream_id);
+        noise_mask_kernel<<<(unsigned)((n_mask / 4 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(mask, n_mask, keep_prob, seed, offset, stream_id,
+                                                                                                  state);
     if (eps && n_eps > 0)
-        noise_normal_kernel<<<(unsigned)((n_eps / 4 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(eps, n_eps, seed, offset, stream_id + 0x80000000u);
+        noise_normal_kernel<<<(unsigned)((n_eps / 4 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(eps, n_eps, seed, offset,
+                                                                                                    stream_id + 0x80000000u, state);
     HVAE_LAUNCH_CHECK("fill_noise");
     return 0;
 }

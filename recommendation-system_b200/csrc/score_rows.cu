@@ -78,29 +78,104 @@ __global__ void __launch_bounds__(256) sparse_dot_xsum_kernel(const int64_t* __r
 
 // dU[b,:] = s_b * sum_p O[p][b,:] - inv_bg * sum_j x_bj E[idx_j,:];  s_b = oscale ? oscale[b] * inv_bg : 1
 // (O may come as n_parts partial sums over item splits, [n_parts][B][ldo], added in a fixed order.)
+// One thread per 4 output columns: the partial sums and the E rows are read as coalesced vectors.
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p, int c, int d);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p, int c, int d) {  // fp32 E has lde == d: no padding, scalar loads
+    float4 r;
+    r.x = c < d ? p[c] : 0.f; r.y = c + 1 < d ? p[c + 1] : 0.f; r.z = c + 2 < d ? p[c + 2] : 0.f; r.w = c + 3 < d ? p[c + 3] : 0.f;
+    return r;
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p, int c, int d) {  // bf16 E rows are zero-padded to 8
+    const uint2 w = *reinterpret_cast<const uint2*>(p + c);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                           const float* __restrict__ values, const int32_t* __restrict__ rows, int B,
                                                           const float* __restrict__ O, int ldo, int n_parts,
                                                           const float* __restrict__ oscale, const T* __restrict__ E, int lde, int d,
                                                           const float* __restrict__ inv_bg, float* __restrict__ dU, int lddu) {
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (b >= B) return;
+    const int ld4 = lddu >> 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * ld4) return;
+    const int b = t / ld4, c = (t - b * ld4) * 4;
     const int u = rows ? rows[b] : b;
     const float ib = *inv_bg, s = oscale ? oscale[b] * ib : 1.0f;
     const size_t pstride = (size_t)B * ldo;
-    const int64_t js = indptr[u], je = indptr[u + 1];
-    for (int c = lane; c < lddu; c += 32) {
-        float g = 0.f;
-        if (c < d) {
-            float a = 0.f;
-            for (int64_t j = js; j < je; ++j) a = fmaf(values ? values[j] : 1.0f, to_f(E[(size_t)indices[j] * lde + c]), a);
-            float o = 0.f;
-            for (int pp = 0; pp < n_parts; ++pp) o += O[pp * pstride + (size_t)b * ldo + c];
-            g = s * o - ib * a;
-        }
-        dU[(size_t)b * lddu + c] = g;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* op = O + (size_t)b * ldo + c;
+    for (int pp = 0; pp < n_parts; ++pp) {
+        const float4 v = *reinterpret_cast<const float4*>(op + pp * pstride);
+        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
     }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t js = indptr[u], je = indptr[u + 1];
+    for (int64_t j = js; j < je; ++j) {
+        const float x = values ? values[j] : 1.0f;
+        const float4 e = load4<T>(E + (size_t)indices[j] * lde, c, d);
+        a.x = fmaf(x, e.x, a.x); a.y = fmaf(x, e.y, a.y); a.z = fmaf(x, e.z, a.z); a.w = fmaf(x, e.w, a.w);
+    }
+    float4 g;
+    g.x = c < d ? s * o.x - ib * a.x : 0.f;
+    g.y = c + 1 < d ? s * o.y - ib * a.y : 0.f;
+    g.z = c + 2 < d ? s * o.z - ib * a.z : 0.f;
+    g.w = c + 3 < d ? s * o.w - ib * a.w : 0.f;
+    *reinterpret_cast<float4*>(dU + (size_t)b * lddu + c) = g;
+}
+
+// bf16 fast path of sparse_dot_xsum: U row chunks live in registers, E rows are read as 16-byte vectors.
+__global__ void __launch_bounds__(256) sparse_dot_xsum_bf16_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                                   const float* __restrict__ values, const int32_t* __restrict__ rows,
+                                                                   int B, const __nv_bfloat16* __restrict__ U, int ldu,
+                                                                   const __nv_bfloat16* __restrict__ E, int lde, int nchunks,
+                                                                   float* __restrict__ dot, float* __restrict__ xsum) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int u = rows ? rows[b] : b;
+    float ur[4][8];
+#pragma unroll
+    for (int pss = 0; pss < 4; ++pss) {
+        const int ch = lane + 32 * pss;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (ch < nchunks) w = *reinterpret_cast<const uint4*>(U + (size_t)b * ldu + ch * 8);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+            ur[pss][2 * e] = f.x; ur[pss][2 * e + 1] = f.y;
+        }
+    }
+    float acc = 0.f, xs = 0.f;
+    const int64_t js = indptr[u], je = indptr[u + 1];
+    for (int64_t j = js; j < je; ++j) {
+        const float x = values ? values[j] : 1.0f;
+        const __nv_bfloat16* e = E + (size_t)indices[j] * lde;
+        float p = 0.f;
+#pragma unroll
+        for (int pss = 0; pss < 4; ++pss) {
+            const int ch = lane + 32 * pss;
+            if (ch < nchunks) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4*>(e + ch * 8));
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[q]));
+                    p = fmaf(ur[pss][2 * q], f.x, p);
+                    p = fmaf(ur[pss][2 * q + 1], f.y, p);
+                }
+            }
+        }
+        acc = fmaf(x, p, acc);
+        xs += x;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) { dot[b] = acc; xsum[b] = xs; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -293,7 +368,10 @@ int hvae_row_softmax_scale(float* S, int64_t lds, int rows, int N, const float* 
 int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
                          const void* U, int ldu, const void* E, int lde, int d, int is_bf16, float* dot, float* xsum, void* stream) {
     if (B == 0) return 0;
-    if (is_bf16)
+    if (is_bf16 && ldu % 8 == 0 && lde % 8 == 0 && d <= 1024)
+        sparse_dot_xsum_bf16_kernel<<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
+            indptr, indices, values, rows, B, (const __nv_bfloat16*)U, ldu, (const __nv_bfloat16*)E, lde, ceil_div(d, 8), dot, xsum);
+    else if (is_bf16)
         sparse_dot_xsum_kernel<__nv_bfloat16><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
             indptr, indices, values, rows, B, (const __nv_bfloat16*)U, ldu, (const __nv_bfloat16*)E, lde, d, dot, xsum);
     else
@@ -307,11 +385,13 @@ int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float*
                      int ldo, int n_parts, const float* oscale, const void* E, int lde, int d, int is_bf16, const float* inv_bg,
                      float* dU, int lddu, void* stream) {
     if (B == 0) return 0;
+    HVAE_REQUIRE(lddu % 4 == 0 && ldo % 4 == 0 && (!is_bf16 || lde % 8 == 0), "du_finalize: leading dimensions must be multiples of 4 (bf16 E: 8)");
+    const int nb = ceil_div(B * (lddu / 4), 256);
     if (is_bf16)
-        du_finalize_kernel<__nv_bfloat16><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
+        du_finalize_kernel<__nv_bfloat16><<<nb, 256, 0, (cudaStream_t)stream>>>(
             indptr, indices, values, rows, B, O, ldo, n_parts, oscale, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
     else
-        du_finalize_kernel<float><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
+        du_finalize_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
                                                                                    (const float*)E, lde, d, inv_bg, dU, lddu);
     HVAE_LAUNCH_CHECK("du_finalize");
     return 0;

@@ -44,7 +44,7 @@ class StepState(ctypes.Structure):
     _fields_ = [("adam_step", ctypes.c_int32), ("anneal_step", ctypes.c_int32), ("step_size", ctypes.c_float),
                 ("bc2_sqrt", ctypes.c_float), ("beta_kl", ctypes.c_float), ("inv_bg", ctypes.c_float),
                 ("kl_coef", ctypes.c_float), ("clip_coef", ctypes.c_float), ("grad_norm", ctypes.c_float),
-                ("norm2", ctypes.c_float)]
+                ("norm2", ctypes.c_float), ("noise_lo", ctypes.c_uint32), ("noise_hi", ctypes.c_uint32)]
 
 
 STATE_WORDS = ctypes.sizeof(StepState) // 4

@@ -120,6 +120,7 @@ class Workspace:
 
     def __init__(self, device):
         self.device, self.buf = device, {}
+        self.generation = 0      # bumped whenever a buffer is (re)allocated: captured CUDA graphs hold raw pointers
 
     def get(self, name, shape, dtype=torch.float32, zero=False, fill=None):
         n = int(np.prod(shape)) if len(shape) else 1
@@ -131,7 +132,7 @@ class Workspace:
             if fill is not None:
                 t.fill_(fill)
             self.buf[name] = t
-            self.generation = getattr(self, "generation", 0) + 1
+            self.generation += 1
         return t[:n].view(*shape) if len(shape) else t[:1]
 
 
@@ -382,9 +383,9 @@ class Engine:
         return tc.score_loss_bf16(self, batch, u, want_grad)
 
     # -- one full training step ---------------------------------------------------------------------------------
-    def begin(self, b_global, lr=1e-3, beta_min=0.0, beta_max=0.2, anneal_steps=0, advance=True):
+    def begin(self, b_global, lr=1e-3, beta_min=0.0, beta_max=0.2, anneal_steps=0, advance=True, noise_stride=0):
         self.lib.step_begin(p(self.state), lr, self.ADAM_B1, self.ADAM_B2, beta_min, beta_max, anneal_steps, b_global,
-                            1 if advance else 0, self.stream)
+                            1 if advance else 0, int(noise_stride), self.stream)
 
     def forward_loss(self, batch: Batch, noise=None, want_grad=False, accumulate=True):
         """Forward + loss.  noise = dict(masks=[uint8 [B,h_i]...], eps=f32 [B,L], pmask=uint8 [B,d]) or None."""
@@ -493,13 +494,13 @@ class Engine:
         return gs, rn2, n_unique, arr["uniq_item"]
 
     def train_step(self, batch: Batch, noise, lr=1e-3, weight_decay=0.0, beta_min=0.0, beta_max=0.2, anneal_steps=0,
-                   b_global=None):
+                   b_global=None, noise_stride=0):
         """zero_grad + forward + loss + backward + clip_grad_norm_(5) + Adam (src/ml/train.py:88-92), fused."""
         self.ensure_optimizer()
         lib, st, lay = self.lib, self.stream, self.lay
         b_global = batch.B if b_global is None else b_global
         self.b_global = b_global
-        self.begin(b_global, lr, beta_min, beta_max, anneal_steps, advance=True)
+        self.begin(b_global, lr, beta_min, beta_max, anneal_steps, advance=True, noise_stride=noise_stride)
         ml, u, O, oscale = self.forward_loss(batch, noise, want_grad=True)
         with self.span("bwd_dense"):
             self.backward(batch, noise, ml, O, oscale)

@@ -164,6 +164,7 @@ class VAETrainer:
         self._noise_ctr = 0
         self._loaders = {}
         self._graphs = {}
+        self._anneal_dev = 0        # device copy of AnnealedVAE.current_step (hvae_step_state.anneal_step)
         logger.info("Trainer on %s, %s params", device, f"{self.model.num_parameters():,}")
 
     # -- multi-GPU ---------------------------------------------------------------------------------------------
@@ -199,27 +200,34 @@ class VAETrainer:
             yield self.model._as_batch(x.to(self.device))
 
     # -- noise ---------------------------------------------------------------------------------------------------
+    def _noise_stride(self, B):
+        m = self.model
+        return (B * max(max(m.hidden_dims), m.embedding_dim, m.latent_dim) + 3) // 4
+
     def _noise(self, B):
+        """Dropout keep-masks and eps for one step.  "philox": counter-based generator inside our kernels; the
+        counter base lives in the device step state and is advanced by step_begin, so a captured CUDA graph draws
+        fresh noise on every replay.  "torch": torch's CUDA generator in the reference's draw order."""
         m = self.model
         if self.noise_mode == "torch":
             return m._draw_noise(B)
         eng, lay = m.engine, m.layout
         keep = 1.0 - m.dropout
+        seed, stp = self._noise_seed, p(eng.state)
         masks = []
         for i, h in enumerate(m.hidden_dims):
             if m.dropout > 0:
                 mk = eng.ws.get(f"mask{i}", (B, h), torch.uint8)
-                eng.lib.fill_noise(p(mk), B * h, keep, None, 0, self._noise_seed, self._noise_ctr, 1 + i, eng.stream)
+                eng.lib.fill_noise(p(mk), B * h, keep, None, 0, seed, 0, 1 + i, stp, eng.stream)
                 masks.append(mk)
             else:
                 masks.append(None)
         eps = eng.ws.get("eps", (B, m.latent_dim))
-        eng.lib.fill_noise(None, 0, keep, p(eps), B * m.latent_dim, self._noise_seed, self._noise_ctr, 100, eng.stream)
+        eng.lib.fill_noise(None, 0, keep, p(eps), B * m.latent_dim, seed, 0, 100, stp, eng.stream)
         pmask = None
         if not lay.identity_proj and m.dropout > 0:
             pmask = eng.ws.get("pmask", (B, m.embedding_dim), torch.uint8)
-            eng.lib.fill_noise(p(pmask), B * m.embedding_dim, keep, None, 0, self._noise_seed, self._noise_ctr, 200, eng.stream)
-        self._noise_ctr += (B * max(max(m.hidden_dims), m.embedding_dim) + 3) // 4
+            eng.lib.fill_noise(p(pmask), B * m.embedding_dim, keep, None, 0, seed, 0, 200, stp, eng.stream)
         return dict(masks=masks, eps=eps, pmask=pmask)
 
     # -- steps ---------------------------------------------------------------------------------------------------
@@ -229,17 +237,97 @@ class VAETrainer:
             return dict(beta_min=m.beta_min, beta_max=m.beta_max, anneal_steps=int(m.anneal_steps))
         return dict(beta_min=0.0, beta_max=m.beta, anneal_steps=0)
 
+    def _sync_anneal_step(self):
+        """AnnealedVAE.current_step is a host attribute (src/ml/model.py:310); the kernels keep their own copy in the
+        device step state and advance it themselves.  Write it only when the host value was changed from outside."""
+        m, eng = self.model, self.model.engine
+        if hasattr(m, "current_step") and int(m.current_step) != self._anneal_dev:
+            eng.state[STATE_OFF["anneal_step"]:STATE_OFF["anneal_step"] + 1].view(torch.int32).fill_(int(m.current_step))
+            self._anneal_dev = int(m.current_step)
+
+    def _eager_step(self, batch: Batch, noise, b_global):
+        eng = self.model.engine
+        own_noise = noise is None
+        if own_noise:
+            noise = self._noise(batch.B)
+        eng.train_step(batch, noise, lr=self.lr, weight_decay=self.weight_decay, b_global=b_global,
+                       noise_stride=self._noise_stride(batch.B) if own_noise else 0, **self._anneal())
+
+    def _graph_entry(self, kind, batch: Batch, b_global):
+        """Static input buffers + captured graph of one step for this (batch size, nnz bound)."""
+        eng = self.model.engine
+        cap = max(1024, -(-int(batch.nnz_cap * 1.05) // 1024) * 1024)        # bucketed so that re-captures are rare
+        key = (kind, batch.B, b_global, self.lr, self.weight_decay)
+        ent = self._graphs.get(key)
+        if ent is not None and ent["cap"] >= batch.nnz_cap and ent["gen"] == eng.ws.generation:
+            return ent
+        dev, B = self.device, batch.B
+        ent = {"cap": cap, "graph": None, "launches": 0, "gen": eng.ws.generation}
+        if kind == "rows":      # batch = user ids into the resident CSR
+            ent["rows"] = torch.zeros(B, dtype=torch.int32, device=dev)
+            ent["batch"] = Batch(batch.csr, ent["rows"], B, cap, b_global=batch.b_global, nnz_cap_global=batch.nnz_cap_global)
+            ent["csr_id"] = id(batch.csr)
+        else:                   # batch = its own CSR slice copied from the host every step
+            ent["crow"] = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+            ent["col"] = torch.zeros(cap, dtype=torch.int32, device=dev)
+            ent["val"] = torch.ones(cap, dtype=torch.float32, device=dev)
+            ent["batch"] = Batch(DeviceCSR(ent["crow"], ent["col"], ent["val"], B, self.model.n_items, None), None, B, cap)
+        self._graphs[key] = ent
+        return ent
+
+    def _load_static(self, ent, batch: Batch):
+        if "rows" in ent:
+            ent["rows"].copy_(batch.rows, non_blocking=True)
+        else:
+            nnz = batch.csr.indices.shape[0]
+            ent["crow"].copy_(batch.csr.indptr, non_blocking=True)
+            ent["col"][:nnz].copy_(batch.csr.indices, non_blocking=True)
+            if batch.csr.values is None:
+                ent["val"][:nnz].fill_(1.0)
+            else:
+                ent["val"][:nnz].copy_(batch.csr.values, non_blocking=True)
+
+    def _graphed_step(self, batch: Batch, b_global):
+        eng = self.model.engine
+        kind = "rows" if batch.rows is not None else "csr"
+        ent = self._graph_entry(kind, batch, b_global)
+        if kind == "rows" and ent.get("csr_id") != id(batch.csr):
+            self._graphs.pop((kind, batch.B, b_global, self.lr, self.weight_decay), None)
+            ent = self._graph_entry(kind, batch, b_global)
+        self._load_static(ent, batch)
+        self._run_entry(ent, b_global)
+
+    def _run_entry(self, ent, b_global):
+        eng = self.model.engine
+        if ent["graph"] is None:
+            # first use: one eager step on the static buffers (allocates every workspace), then capture for the next ones
+            self._eager_step(ent["batch"], None, b_global)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            l0 = eng.lib.launches
+            with torch.cuda.graph(g):
+                self._eager_step(ent["batch"], None, b_global)
+            ent["launches"] = eng.lib.launches - l0
+            eng.lib.launches = l0
+            ent["graph"], ent["gen"] = g, eng.ws.generation
+            return
+        ent["graph"].replay()
+        eng.lib.launches += ent["launches"]
+
     def train_step(self, batch: Batch, noise=None, b_global=None):
         """One optimisation step on a sparse batch; `noise` overrides the trainer's RNG (parity tests)."""
         m = self.model
         eng = m.engine
-        if noise is None:
-            noise = self._noise(batch.B)
-        if hasattr(m, "current_step"):
-            eng.state[STATE_OFF["anneal_step"]:STATE_OFF["anneal_step"] + 1].view(torch.int32).fill_(int(m.current_step))
-        eng.train_step(batch, noise, lr=self.lr, weight_decay=self.weight_decay, b_global=b_global, **self._anneal())
+        self._sync_anneal_step()
+        graphable = (noise is None and self.use_cuda_graph and self.noise_mode == "philox" and eng.dist is None
+                     and eng.prof is None)
+        if graphable:
+            self._graphed_step(batch, b_global)
+        else:
+            self._eager_step(batch, noise, b_global)
         if hasattr(m, "current_step"):
             m.step_annealing()
+            self._anneal_dev += 1
 
     def _host_batch(self, x) -> Batch:
         """HOST (ideally pinned) or device batch -> device Batch.  Sparse CSR tensors are copied as their three
@@ -257,11 +345,30 @@ class VAETrainer:
             return Batch(csr, None, x.shape[0], max(1, nnz))
         return self.model._as_batch(x.to(self.device, non_blocking=True))
 
+    def _host_csr_step(self, x, b_global):
+        """Host CSR batch -> static device buffers (one H2D copy per array) -> replay of the captured step."""
+        crow, col, val = x.crow_indices(), x.col_indices(), x.values()
+        nnz, B = int(col.shape[0]), x.shape[0]
+        ent = self._graph_entry("csr", Batch(None, None, B, max(1, nnz)), b_global)
+        ent["crow"].copy_(crow, non_blocking=True)
+        ent["col"][:nnz].copy_(col, non_blocking=True)
+        ent["val"][:nnz].copy_(val, non_blocking=True)
+        self._run_entry(ent, b_global)
+
     def train_on_batch(self, x, b_global=None) -> dict[str, float]:
         """One iteration of the reference loop (src/ml/train.py:86-96) on one batch: host->device copy of the
         batch, the fused step, and the three loss scalars read back (the reference's three .item() calls)."""
         self.model.train()
-        self.train_step(self._host_batch(x), b_global=b_global)
+        eng = self.model.engine
+        if (isinstance(x, torch.Tensor) and x.layout == torch.sparse_csr and not x.is_cuda and self.use_cuda_graph
+                and self.noise_mode == "philox" and eng.dist is None and eng.prof is None):
+            self._sync_anneal_step()
+            self._host_csr_step(x, b_global)
+            if hasattr(self.model, "current_step"):
+                self.model.step_annealing()
+                self._anneal_dev += 1
+        else:
+            self.train_step(self._host_batch(x), b_global=b_global)
         total, recon, kl = self.last_losses()
         return {"total_loss": total, "recon_loss": recon, "kl_loss": kl}
 

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in decls:
         assert hasattr(dll, name), name
     assert _cabi.lib().abi_version() == 1
-    assert ctypes.sizeof(_cabi.StepState) == 40
+    assert ctypes.sizeof(_cabi.StepState) == 48
 
 
 @pytest.mark.parametrize("name", TRAIN_CASES)

@@ -338,3 +338,25 @@ def test_bf16_c1_shape_eval_within_tolerance(dev):
     assert np.abs(got - g["metrics"]).max() < 1e-3 + 1.0 / len(users)
     overlap = np.mean([len(set(a) & set(b)) / len(b) for a, b in zip(idx.cpu().numpy(), g["topk"])])
     assert overlap > 0.97
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_step_equals_eager(dev, precision):
+    """The captured step (static buffers, device-side noise counter) replays to exactly what eager launches give."""
+    from hvae_b200.train import CSRLoader, VAETrainer
+    c = Case("tiny_annealed")
+    out = []
+    for graph in (False, True):
+        torch.manual_seed(3)
+        m = _build(c, dev, precision=precision)
+        tr = VAETrainer(m, dev, lr=1e-3, use_cuda_graph=graph)
+        tr._noise_seed = 1234
+        ld = CSRLoader(c.csr, list(range(c.n_users - c.n_users % 32)), 32, False, dev)
+        losses = [tr.train_epoch(ld) for _ in range(3)]
+        out.append((losses, {k: v.cpu() for k, v in m.state_dict().items()}, m.current_step))
+    (l0, s0, a0), (l1, s1, a1) = out
+    assert a0 == a1 and a0 > 0
+    for d0, d1 in zip(l0, l1):
+        assert d0 == d1
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), k
