@@ -321,34 +321,44 @@ def main():
     # ---- timed region 2 (`e2e`): public API with HOST (pinned) batches; H2D of the batch and D2H of the loss every step
     KE = min(K, 200)
     host_batches = []
-    for s in range(KE):
-        g0 = (s % n_batches) * Bg
-        rows_h = order[g0 + rank * B:g0 + (rank + 1) * B].astype(np.int64)
-        starts, ln = data.indptr[rows_h], lens[rows_h]
-        crow = np.zeros(B + 1, dtype=np.int64)
-        np.cumsum(ln, out=crow[1:])
-        take = np.repeat(starts - crow[:-1], ln) + np.arange(int(ln.sum()), dtype=np.int64)
-        col = data.indices[take].astype(np.int32)
-        x = torch.sparse_csr_tensor(torch.from_numpy(crow).pin_memory(), torch.from_numpy(col).pin_memory(),
-                                    torch.ones(col.shape[0], dtype=torch.float32).pin_memory(), size=(B, N), check_invariants=False)
-        host_batches.append(x)
-    h2d = float(np.mean([x.crow_indices().numel() * 8 + x.col_indices().numel() * 4 + x.values().numel() * 4 for x in host_batches]))
+    if world == 1:      # the step's input is the batch's CSR slice (indptr, indices, values) in pinned host memory
+        for s in range(KE):
+            g0 = (s % n_batches) * Bg
+            rows_h = order[g0 + rank * B:g0 + (rank + 1) * B].astype(np.int64)
+            starts, ln = data.indptr[rows_h], lens[rows_h]
+            crow = np.zeros(B + 1, dtype=np.int64)
+            np.cumsum(ln, out=crow[1:])
+            take = np.repeat(starts - crow[:-1], ln) + np.arange(int(ln.sum()), dtype=np.int64)
+            col = data.indices[take].astype(np.int32)
+            x = torch.sparse_csr_tensor(torch.from_numpy(crow).pin_memory(), torch.from_numpy(col).pin_memory(),
+                                        torch.ones(col.shape[0], dtype=torch.float32).pin_memory(), size=(B, N), check_invariants=False)
+            host_batches.append(x)
+        h2d = float(np.mean([x.crow_indices().numel() * 8 + x.col_indices().numel() * 4 + x.values().numel() * 4 for x in host_batches]))
+        e2e_api = "VAETrainer.train_on_batch(pinned host CSR batch) -> loss floats"
+    else:               # data parallel: the interaction CSR is resident on every rank; the step's input is its user ids
+        trainer.set_interactions(csr)
+        for s in range(KE):
+            g0 = (s % n_batches) * Bg
+            host_batches.append(torch.from_numpy(order[g0 + rank * B:g0 + (rank + 1) * B].copy()).pin_memory())
+        h2d = float(B * 4)
+        e2e_api = "VAETrainer.train_on_batch(pinned host user-id batch into the resident CSR) -> loss floats"
+    capg = cap_global if world > 1 else None
     for s in range(3):
-        trainer.train_on_batch(host_batches[s], b_global=Bg)
+        trainer.train_on_batch(host_batches[s], b_global=Bg, nnz_cap_global=capg)
     barrier()
     t_e2e = 0.0
     for s in range(KE):
         flush_buf.fill_(s & 0xFF)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        trainer.train_on_batch(host_batches[s], b_global=Bg)     # returns python floats -> synchronises
+        trainer.train_on_batch(host_batches[s], b_global=Bg, nnz_cap_global=capg)     # returns python floats -> synchronises
         t_e2e += time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t[0])
     e2e = {"value": KE * Bg / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12, "steps": KE,
-           "api": "VAETrainer.train_on_batch(pinned host CSR batch) -> loss floats"}
+           "api": e2e_api}
 
     # ---- evaluation: full-ranking top-K + Recall/NDCG/HR over every user (evaluate.py:243-265), user-sharded over ranks
     ev_out = None

@@ -4,14 +4,13 @@
 // layers (fc_mu/fc_logvar, projection MLP, deeper hidden layers; reference src/ml/model.py:90-95,114,126-127)
 // forward and backward, and the materialised-score path (decode(), src/ml/model.py:198).
 // Two tile shapes: 128x64 for large problems, 32x64 when the large tile would leave most of the 148 SMs idle
-// (the MLP GEMMs of a 512-user batch are 400-600 wide: latency-bound, so CTA count matters more than reuse).
+// (the MLP GEMMs of a 512-user batch are 400-600 wide: latency-bound, so CTA count matters more than reuse; the
+// small tile stages 64-deep k-blocks so that one prefetch covers the HBM latency).
 #include "common.cuh"
 
 namespace hvae {
 
-constexpr int GBK = 16;
-
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int TM, int TN, int GBK>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, int64_t a_rs,
                                                                          int64_t a_cs, const float* __restrict__ Bm, int64_t b_rs,
                                                                          int64_t b_cs, float* __restrict__ C, int64_t ldc,
@@ -111,11 +110,11 @@ extern "C" int hvae_gemm_f32(int M, int N, int K, const float* A, int64_t a_rs, 
     if (big_ctas >= 2 * kNumSMs) {
         dim3 grid(ceil_div(N, 64), ceil_div(M, 128));
         HVAE_REQUIRE(grid.y <= 65535, "gemm_f32: M=%d too large for one launch", M);
-        gemm_f32_kernel<128, 64, 8, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha);
+        gemm_f32_kernel<128, 64, 8, 4, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha);
     } else {
         dim3 grid(ceil_div(N, 64), ceil_div(M, 32));
         HVAE_REQUIRE(grid.y <= 65535, "gemm_f32: M=%d too large for one launch", M);
-        gemm_f32_kernel<32, 64, 4, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha);
+        gemm_f32_kernel<32, 64, 4, 4, 64><<<grid, 128, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha);
     }
     HVAE_LAUNCH_CHECK("gemm_f32");
     return 0;

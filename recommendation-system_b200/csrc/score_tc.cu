@@ -463,12 +463,24 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
 
 constexpr size_t kGradSmem = G_STAGES * G_SLOT + 2 * G_PBYTES + 256 + 1024;
 
-static int pick_grad_splits(int m_tiles, int n_chunks, int n_tiles) {
-    const int want = (2 * kNumSMs) / (m_tiles * n_chunks);
-    const int splits = max(1, min(n_tiles, want));
-    const int tps = (n_tiles + splits - 1) / splits;
+// Item splits per (user tile, column chunk): one CTA per SM in a single wave when each CTA would otherwise get only a
+// few tiles (the prologue -- barrier init, TMEM alloc, first TMA -- costs about one tile), two waves for long CTAs.
+static int pick_wave_splits(int units, int n_tiles) {
+    units = max(1, units);
+    int splits = max(1, min(n_tiles, kNumSMs / units));
+    int tps = (n_tiles + splits - 1) / splits;
+    if (tps > 16) {   // long CTAs: pick the wave count (<= 6) that fills the last wave best
+        double best = -1.0;
+        for (int k = 1; k <= 6; ++k) {
+            const int sk = max(1, min(n_tiles, (k * kNumSMs) / units));
+            const double util = (double)(units * sk) / (double)(kNumSMs * ((units * sk + kNumSMs - 1) / kNumSMs));
+            if (util > best + 0.02) { best = util; splits = sk; }
+        }
+        tps = (n_tiles + splits - 1) / splits;
+    }
     return (n_tiles + tps - 1) / tps;
 }
+static int pick_grad_splits(int m_tiles, int n_chunks, int n_tiles) { return pick_wave_splits(m_tiles * n_chunks, n_tiles); }
 
 // ---- host: TMA descriptors ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -502,13 +514,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int l
     return 0;
 }
 
-static int pick_splits(int m_tiles, int n_tiles) {
-    // one CTA per (user tile, item split); aim at ~2 waves of 148 SMs without leaving CTAs with < 1 tile
-    int want = (2 * kNumSMs) / m_tiles;
-    int splits = max(1, min(n_tiles, want));
-    const int tps = (n_tiles + splits - 1) / splits;
-    return (n_tiles + tps - 1) / tps;
-}
+static int pick_splits(int m_tiles, int n_tiles) { return pick_wave_splits(m_tiles, n_tiles); }
 
 constexpr size_t kStatsSmem = STAGES * STAGE_BYTES + 256 + BM * MAXK_TC * 8 + 1024;
 

@@ -51,10 +51,11 @@ def gather_candidates(val: torch.Tensor, idx: torch.Tensor, group=None):
     """All-gather per-rank top-K candidates [B, K] -> ([B, G*K] values, [B, G*K] global ids), rank-major."""
     world = dist.get_world_size(group)
     B, K = val.shape
-    gv = torch.empty(world, B, K, dtype=val.dtype, device=val.device)
-    gi = torch.empty(world, B, K, dtype=idx.dtype, device=idx.device)
+    gv = torch.empty(world * B, K, dtype=val.dtype, device=val.device)      # concatenation along dim 0 (gloo and nccl)
+    gi = torch.empty(world * B, K, dtype=idx.dtype, device=idx.device)
     dist.all_gather_into_tensor(gv, val.contiguous(), group=group)
     dist.all_gather_into_tensor(gi, idx.contiguous(), group=group)
+    gv, gi = gv.view(world, B, K), gi.view(world, B, K)
     return gv.permute(1, 0, 2).reshape(B, world * K).contiguous(), gi.permute(1, 0, 2).reshape(B, world * K).contiguous()
 
 

@@ -7,6 +7,7 @@ torch's current stream.  PyTorch is used for allocation, streams and CUDA-graph 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from dataclasses import dataclass
 
@@ -234,9 +235,31 @@ class Engine:
         self.dist = None  # set by hvae_b200.dist for data-parallel training
         self._E_bf16 = None
         self.prof = None  # dict name -> [(start, stop) events] when profiling spans are enabled
+        self.concurrent, self._side, self._forked = False, [], set()
 
     def span(self, name):
         return _Span(self, name)
+
+    # -- concurrency inside a captured step: independent kernels go to side streams (fork/join edges of the CUDA graph)
+    def side(self, i):
+        """Context manager: run the enclosed launches on side stream i, ordered after everything enqueued so far on
+        the main stream.  Only active while `self.concurrent` (set by the trainer around graph capture)."""
+        if not self.concurrent:
+            return contextlib.nullcontext()
+        while len(self._side) <= i:
+            self._side.append(torch.cuda.Stream(self.dev))
+        st = self._side[i]
+        st.wait_stream(torch.cuda.current_stream(self.dev))
+        self._forked.add(i)
+        return torch.cuda.stream(st)
+
+    def join(self):
+        """Main stream waits for every side stream used since the last join."""
+        if self._forked:
+            cur = torch.cuda.current_stream(self.dev)
+            for i in sorted(self._forked):
+                cur.wait_stream(self._side[i])
+            self._forked.clear()
 
     def span_ms(self):
         """{name: [ms per occurrence]} of the recorded spans (synchronises)."""
@@ -395,6 +418,7 @@ class Engine:
                                     None if noise is None else noise.get("pmask"))
         with self.span("score"):
             lse, dot, xsum, O, oscale = self.score_loss(batch, u, want_grad)
+        self.join()
         self.lib.loss_finalize(p(lse), p(dot), p(xsum), p(self.ws.get("kl_row", (batch.B,))), batch.B, self.state_ptr("inv_bg"),
                                self.state_ptr("beta_kl"), p(self.loss_out), p(self.acc) if accumulate else None, self.stream)
         return ml, u, O, oscale
@@ -408,7 +432,8 @@ class Engine:
         masks = None if noise is None else noise["masks"]
         eps = None if noise is None else noise["eps"]
         pmask = None if noise is None else noise.get("pmask")
-        cs_ws = ws.get("colsum_ws", (64 * max(max(h), 2 * L, d) + 64,))
+        cs_ws = ws.get("colsum_ws", (64 * max(max(h), 2 * L, d) + 64,))     # side stream 1 only
+        cs_ws2 = cs_ws                                                      # (same stream -> same scratch is safe)
         if du_override is not None:
             dU = du_override
         else:
@@ -423,16 +448,21 @@ class Engine:
         else:
             q, t, z = ws.get("q", (B, ldd)), ws.get("t", (B, ldd)), ws.get("z", (B, ldz))
             w0, w3 = lay.slots["projection_layer.0.weight"], lay.slots["projection_layer.3.weight"]
-            # dWp3 = dU^T t ; dbp3 = colsum(dU) ; dt = dU Wp3
-            self.gemm(d, d, B, p(dU), 1, ldd, p(t), ldd, 1, self.G("projection_layer.3.weight"), w3.ld)
-            lib.colsum(p(dU), ldd, B, d, self.G("projection_layer.3.bias"), p(cs_ws), st)
+            # dWp3 = dU^T t ; dbp3 = colsum(dU) ; dt = dU Wp3   (three independent kernels: side streams 0/1 + main)
+            with self.side(0):
+                self.gemm(d, d, B, p(dU), 1, ldd, p(t), ldd, 1, self.G("projection_layer.3.weight"), w3.ld)
+            with self.side(1):
+                lib.colsum(p(dU), ldd, B, d, self.G("projection_layer.3.bias"), p(cs_ws), self.stream)
             dt = ws.get("dt", (B, ldd))
             self.gemm(B, d, d, p(dU), ldd, 1, self.P("projection_layer.3.weight"), w3.ld, 1, p(dt), ldd)
-            lib.gelu_drop_bwd(p(dt), p(q), p(pmask), self.keep_scale, B, d, ldd, p(dt), st)       # dt becomes dq
-            self.gemm(d, L, B, p(dt), 1, ldd, p(z), ldz, 1, self.G("projection_layer.0.weight"), w0.ld)
-            lib.colsum(p(dt), ldd, B, d, self.G("projection_layer.0.bias"), p(cs_ws), st)
+            dq = ws.get("dq", (B, ldd))
+            lib.gelu_drop_bwd(p(dt), p(q), p(pmask), self.keep_scale, B, d, ldd, p(dq), st)
+            with self.side(0):
+                self.gemm(d, L, B, p(dq), 1, ldd, p(z), ldz, 1, self.G("projection_layer.0.weight"), w0.ld)
+            with self.side(1):
+                lib.colsum(p(dq), ldd, B, d, self.G("projection_layer.0.bias"), p(cs_ws2), self.stream)
             dz = ws.get("dz", (B, ldz))
-            self.gemm(B, L, d, p(dt), ldd, 1, self.P("projection_layer.0.weight"), w0.ld, 1, p(dz), ldz)
+            self.gemm(B, L, d, p(dq), ldd, 1, self.P("projection_layer.0.weight"), w0.ld, 1, p(dz), ldz)
         dml = ws.get("dml", (B, ldml))
         lib.latent_bwd(p(dz), ldz, p(ml), ldml, p(eps), B, L, self.state_ptr("kl_coef") if ext_dml is None else p(self._zero()),
                        p(dml), st)
@@ -441,8 +471,10 @@ class Engine:
         wm = lay.slots["fc_mu.weight"]
         nh = len(h)
         act_last = ws.get(f"act{nh - 1}", (B, r4(h[-1])))
-        self.gemm(2 * L, h[-1], B, p(dml), 1, ldml, p(act_last), r4(h[-1]), 1, self.G("fc_mu.weight"), wm.ld)
-        lib.colsum(p(dml), ldml, B, 2 * L, self.G("fc_ml.bias"), p(cs_ws), st)
+        with self.side(0):
+            self.gemm(2 * L, h[-1], B, p(dml), 1, ldml, p(act_last), r4(h[-1]), 1, self.G("fc_mu.weight"), wm.ld)
+        with self.side(1):
+            lib.colsum(p(dml), ldml, B, 2 * L, self.G("fc_ml.bias"), p(cs_ws), self.stream)
         dact = ws.get(f"dact{nh - 1}", (B, r4(h[-1])))
         self.gemm(B, h[-1], 2 * L, p(dml), ldml, 1, self.P("fc_mu.weight"), wm.ld, 1, p(dact), r4(h[-1]))
         ln_ws = ws.get("ln_ws", (max(lib.ln_bwd_workspace_floats(B, r4(hh)) for hh in h),))
@@ -452,11 +484,13 @@ class Engine:
             gk, bk = (f"encoder.{4 * i + 1}.weight", f"encoder.{4 * i + 1}.bias")
             lib.ln_act_bwd(p(dact), p(pre), p(mean), p(rstd), self.P(gk), self.P(bk), p(None if masks is None else masks[i]),
                            self.keep_scale, B, hi, ld, p(dact), self.G(gk), self.G(bk), p(ln_ws), st)   # dact becomes dpre
-            lib.colsum(p(dact), ld, B, hi, self.G(f"encoder.{4 * i}.bias"), p(cs_ws), st)
+            with self.side(1):
+                lib.colsum(p(dact), ld, B, hi, self.G(f"encoder.{4 * i}.bias"), p(cs_ws), self.stream)
             if i > 0:
                 w = lay.slots[f"encoder.{4 * i}.weight"]
                 prev = ws.get(f"act{i - 1}", (B, r4(h[i - 1])))
-                self.gemm(hi, h[i - 1], B, p(dact), 1, ld, p(prev), r4(h[i - 1]), 1, self.G(f"encoder.{4 * i}.weight"), w.ld)
+                with self.side(0):
+                    self.gemm(hi, h[i - 1], B, p(dact), 1, ld, p(prev), r4(h[i - 1]), 1, self.G(f"encoder.{4 * i}.weight"), w.ld)
                 dprev = ws.get(f"dact{i - 1}", (B, r4(h[i - 1])))
                 self.gemm(B, h[i - 1], hi, p(dact), ld, 1, self.P(f"encoder.{4 * i}.weight"), w.ld, 1, p(dprev), r4(h[i - 1]))
                 dact = dprev
@@ -467,11 +501,12 @@ class Engine:
     def _zero(self):
         return self.ws.get("zero1", (1,), zero=True)
 
-    def sparse_w1_grad(self, batch: Batch, dpre0, B=None):
-        """Transpose the batch by item and reduce d(W1^T) rows (deterministic)."""
+    def transpose_batch(self, batch: Batch):
+        """Sort the batch's (user, item, value) entries by item (stable): segment s = the entries of touched item s.
+        Depends on the batch only, so a captured step runs it beside the forward pass."""
         lay, ws, lib, st = self.lay, self.ws, self.lib, self.stream
-        B = batch.B if B is None else B
-        csr, cap, ld1 = batch.csr, batch.nnz_cap, r4(lay.hidden[0])
+        B = batch.B
+        csr, cap = batch.csr, batch.nnz_cap
         i32 = torch.int32
         boff = ws.get("boff", (B + 1,), i32)
         names = ["keys", "keys_sorted", "eid", "eid_sorted", "head", "slot", "ent_user", "uniq_item"]
@@ -482,16 +517,29 @@ class Engine:
         overflow = ws.get("bt_overflow", (1,), i32, zero=True)
         tb = int(lib.batch_temp_bytes(cap, lay.N))
         temp = ws.get("bt_temp", (tb,), torch.uint8)
-        gs = ws.get("gs", (cap, ld1))
-        rn2 = ws.get("rownorm2", (cap,))
         lib.batch_offsets(p(csr.indptr), p(batch.rows), B, p(boff), st)
         lib.batch_transpose(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, lay.N, cap, p(boff), p(arr["keys"]),
                             p(arr["keys_sorted"]), p(arr["eid"]), p(arr["eid_sorted"]), p(arr["head"]), p(arr["slot"]),
                             p(arr["ent_user"]), p(ent_val), p(seg_start), p(arr["uniq_item"]), p(self.slot_of_item), p(n_unique),
                             p(overflow), p(temp), tb, st)
-        lib.w1_grad(p(seg_start), p(n_unique), p(arr["eid_sorted"]), p(arr["ent_user"]), p(ent_val), cap, p(dpre0), ld1, p(gs),
-                    p(rn2), st)
-        return gs, rn2, n_unique, arr["uniq_item"]
+        return dict(cap=cap, seg_start=seg_start, n_unique=n_unique, eid_sorted=arr["eid_sorted"], ent_user=arr["ent_user"],
+                    ent_val=ent_val, uniq=arr["uniq_item"])
+
+    def w1_grad(self, tb, dpre0):
+        """d(W1^T) rows of the touched items (deterministic segment sums) and their squared norms."""
+        ws, lib = self.ws, self.lib
+        ld1 = r4(self.lay.hidden[0])
+        gs = ws.get("gs", (tb["cap"], ld1))
+        rn2 = ws.get("rownorm2", (tb["cap"],))
+        lib.w1_grad(p(tb["seg_start"]), p(tb["n_unique"]), p(tb["eid_sorted"]), p(tb["ent_user"]), p(tb["ent_val"]), tb["cap"],
+                    p(dpre0), ld1, p(gs), p(rn2), self.stream)
+        return gs, rn2
+
+    def sparse_w1_grad(self, batch: Batch, dpre0, B=None):
+        """Transpose the batch by item and reduce d(W1^T) rows (deterministic)."""
+        tb = self.transpose_batch(batch)
+        gs, rn2 = self.w1_grad(tb, dpre0)
+        return gs, rn2, tb["n_unique"], tb["uniq"]
 
     def train_step(self, batch: Batch, noise, lr=1e-3, weight_decay=0.0, beta_min=0.0, beta_max=0.2, anneal_steps=0,
                    b_global=None, noise_stride=0):
@@ -501,6 +549,10 @@ class Engine:
         b_global = batch.B if b_global is None else b_global
         self.b_global = b_global
         self.begin(b_global, lr, beta_min, beta_max, anneal_steps, advance=True, noise_stride=noise_stride)
+        tb = None
+        if self.dist is None:            # the item-major view of the batch does not depend on the forward pass
+            with self.side(2), self.span("transpose"):
+                tb = self.transpose_batch(batch)
         ml, u, O, oscale = self.forward_loss(batch, noise, want_grad=True)
         with self.span("bwd_dense"):
             self.backward(batch, noise, ml, O, oscale)
@@ -508,8 +560,11 @@ class Engine:
         if self.dist is not None:
             with self.span("exchange"):
                 wbatch, dpre0 = self.dist.exchange(self, batch, dpre0)
+            tb = self.transpose_batch(wbatch)
+        self.join()
         with self.span("w1grad"):
-            gs, rn2, n_unique, uniq = self.sparse_w1_grad(wbatch, dpre0)
+            gs, rn2 = self.w1_grad(tb, dpre0)
+        n_unique, uniq = tb["n_unique"], tb["uniq"]
         gn_ws = self.ws.get("gn_ws", (256,))
         lib.grad_norm_clip(p(self.gd), lay.n_dense, p(rn2), p(n_unique), self.MAX_NORM, p(self.state), p(gn_ws), st)
         with self.span("adam"):

@@ -32,8 +32,9 @@ def score_loss_bf16(eng, batch, u, want_grad):
     Eb = eng.E_bf16
     ub = user_vectors_bf16(eng, u, B)
     lse, dot, xsum = ws.get("lse", (B,)), ws.get("dot", (B,)), ws.get("xsum", (B,))
-    lib.sparse_dot_xsum(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(ub), ld8, p(Eb), ld8, d, 1,
-                        p(dot), p(xsum), st)
+    with eng.side(1):                # independent of the score GEMMs
+        lib.sparse_dot_xsum(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(ub), ld8, p(Eb), ld8, d, 1,
+                            p(dot), p(xsum), eng.stream)
     ns = int(lib.tc_n_splits(B, N))
     wsl = ws.get("tc_lse_ws", (2 * B * ns,))
     with eng.span("score_fwd"):

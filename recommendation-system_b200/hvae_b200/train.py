@@ -305,8 +305,12 @@ class VAETrainer:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             l0 = eng.lib.launches
-            with torch.cuda.graph(g):
-                self._eager_step(ent["batch"], None, b_global)
+            eng.concurrent = True           # independent kernels -> parallel branches of the graph
+            try:
+                with torch.cuda.graph(g):
+                    self._eager_step(ent["batch"], None, b_global)
+            finally:
+                eng.concurrent = False
             ent["launches"] = eng.lib.launches - l0
             eng.lib.launches = l0
             ent["graph"], ent["gen"] = g, eng.ws.generation
@@ -329,11 +333,30 @@ class VAETrainer:
             m.step_annealing()
             self._anneal_dev += 1
 
-    def _host_batch(self, x) -> Batch:
-        """HOST (ideally pinned) or device batch -> device Batch.  Sparse CSR tensors are copied as their three
-        arrays (a few KB per step); dense [B,N] rows are copied whole and compacted on the device."""
+    def set_interactions(self, matrix):
+        """Keep the user x item CSR resident in HBM so that a batch can be named by its user ids alone."""
+        self._resident = matrix if isinstance(matrix, DeviceCSR) else DeviceCSR.from_scipy(matrix, self.device)
+        return self._resident
+
+    def _host_batch(self, x, b_global=None, nnz_cap_global=None) -> Batch:
+        """HOST (ideally pinned) or device batch -> device Batch.  A 1-D integer tensor is a list of user ids into the
+        resident CSR (set_interactions); sparse CSR tensors are copied as their three arrays (a few KB per step);
+        dense [B,N] rows are copied whole and compacted on the device."""
         if isinstance(x, Batch):
             return x
+        if isinstance(x, torch.Tensor) and x.dim() == 1 and not x.dtype.is_floating_point:
+            csr = getattr(self, "_resident", None)
+            if csr is None:
+                raise RuntimeError("user-id batches need trainer.set_interactions(matrix) first")
+            rows_h = x.cpu().numpy() if x.is_cuda else x.numpy()
+            cap = int(csr.host_lengths[rows_h].sum())
+            rows_d = x.to(self.device, torch.int32, non_blocking=True)
+            dp = self.model.engine.dist
+            if dp is not None and nnz_cap_global is None:      # bound of the global batch's nnz: world * max over ranks
+                t = torch.tensor([cap], dtype=torch.int64, device=self.device)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=dp.group)
+                nnz_cap_global = int(t.item()) * dp.world
+            return Batch(csr, rows_d, x.shape[0], max(1, cap), b_global=b_global, nnz_cap_global=nnz_cap_global)
         if isinstance(x, torch.Tensor) and x.layout == torch.sparse_csr:
             crow, col, val = x.crow_indices(), x.col_indices(), x.values()
             nnz = int(col.shape[0])
@@ -355,7 +378,7 @@ class VAETrainer:
         ent["val"][:nnz].copy_(val, non_blocking=True)
         self._run_entry(ent, b_global)
 
-    def train_on_batch(self, x, b_global=None) -> dict[str, float]:
+    def train_on_batch(self, x, b_global=None, nnz_cap_global=None) -> dict[str, float]:
         """One iteration of the reference loop (src/ml/train.py:86-96) on one batch: host->device copy of the
         batch, the fused step, and the three loss scalars read back (the reference's three .item() calls)."""
         self.model.train()
@@ -368,7 +391,9 @@ class VAETrainer:
                 self.model.step_annealing()
                 self._anneal_dev += 1
         else:
-            self.train_step(self._host_batch(x), b_global=b_global)
+            self.train_step(self._host_batch(x, b_global, nnz_cap_global), b_global=b_global)
+        if eng.dist is not None:          # per-rank partial sums (already scaled by 1/B_global) -> global loss
+            torch.distributed.all_reduce(eng.loss_out, group=eng.dist.group)
         total, recon, kl = self.last_losses()
         return {"total_loss": total, "recon_loss": recon, "kl_loss": kl}
 
