@@ -114,6 +114,10 @@ int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, co
                    int32_t* out_idx, void* stream);
 int hvae_topk_merge(const float* cval, const int32_t* cidx, int n_rows, int GK, int K, float* out_val, int32_t* out_idx,
                     void* stream);
+/* Negative-sampling protocol (evaluate.py:149-185): scores of C candidates per row (candidate 0 = test item) and the
+ * 0-based rank of candidate 0 under a stable descending sort.  cand: int32 [B, C]; scores may be NULL. */
+int hvae_candidate_rank(const void* U, int ldu, const void* E, int lde, int d, int is_bf16, const int32_t* cand, int C, int B,
+                        float* scores, int32_t* rank, void* stream);
 /* Recall/NDCG/HR@K (evaluate.py:32-54,90-98) */
 int hvae_hit_mask(const int32_t* topk, int n_rows, int K, const int64_t* rel_ptr, const int32_t* rel_idx, uint32_t* mask,
                   void* stream);

@@ -178,6 +178,29 @@ __global__ void __launch_bounds__(256) sparse_dot_xsum_bf16_kernel(const int64_t
     if (lane == 0) { dot[b] = acc; xsum[b] = xs; }
 }
 
+// Negative-sampling protocol (reference src/ml/evaluate.py:149-185): per row, the scores of C candidate items
+// (candidate 0 = the held-out test item) as C sparse dot products u_b . E_c, and the 0-based rank of candidate 0
+// under a stable descending sort (ties: later candidates first, as argsort(kind="stable")[::-1] orders them).
+template <typename T>
+__global__ void __launch_bounds__(256) candidate_rank_kernel(const T* __restrict__ U, int ldu, const T* __restrict__ E, int lde, int d,
+                                                             const int32_t* __restrict__ cand, int C, int B, float* __restrict__ scores,
+                                                             int32_t* __restrict__ rank) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float s0 = 0.f;
+    int r = 0;
+    for (int c = 0; c < C; ++c) {
+        const T* e = E + (size_t)cand[(size_t)b * C + c] * lde;
+        float p = 0.f;
+        for (int k = lane; k < d; k += 32) p = fmaf(to_f(U[(size_t)b * ldu + k]), to_f(e[k]), p);
+        p = warp_sum(p);
+        if (c == 0) s0 = p;
+        else r += (p >= s0) ? 1 : 0;
+        if (scores && lane == 0) scores[(size_t)b * C + c] = p;
+    }
+    if (lane == 0) rank[b] = r;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // top-K
 __device__ __forceinline__ bool better(float v, int i, float tv, int ti) { return v > tv || (v == tv && i > ti); }
@@ -394,6 +417,20 @@ int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float*
         du_finalize_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
                                                                                    (const float*)E, lde, d, inv_bg, dU, lddu);
     HVAE_LAUNCH_CHECK("du_finalize");
+    return 0;
+}
+
+int hvae_candidate_rank(const void* U, int ldu, const void* E, int lde, int d, int is_bf16, const int32_t* cand, int C, int B,
+                        float* scores, int32_t* rank, void* stream) {
+    if (B == 0) return 0;
+    HVAE_REQUIRE(C >= 1, "candidate_rank: need at least the test item");
+    if (is_bf16)
+        candidate_rank_kernel<__nv_bfloat16><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)U, ldu, (const __nv_bfloat16*)E,
+                                                                                               lde, d, cand, C, B, scores, rank);
+    else
+        candidate_rank_kernel<float><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>((const float*)U, ldu, (const float*)E, lde, d, cand, C, B,
+                                                                                       scores, rank);
+    HVAE_LAUNCH_CHECK("candidate_rank");
     return 0;
 }
 

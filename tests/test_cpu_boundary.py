@@ -135,3 +135,19 @@ def test_metric_functions_match_oracle():
             assert ev.recall_at_k(rec, rel, k) == orc.recall_at_k(rec, rel, k)
             assert ev.ndcg_at_k(rec, rel, k) == orc.ndcg_at_k(rec, rel, k)
             assert ev.hit_ratio_at_k(rec, rel, k) == orc.hit_ratio_at_k(rec, rel, k)
+
+
+def test_negative_sampling_candidates():
+    """99 distinct unseen negatives per row, test item first; short catalogues take what is available
+    (reference src/ml/evaluate.py:160-172)."""
+    from hvae_b200.sampling import sample_negatives
+    from hvae_b200.synth import make_interactions
+    for (U, N) in [(300, 400), (20, 40)]:
+        d = make_interactions(U, N, 1)
+        cand, valid = sample_negatives(d.indptr, d.indices, N, np.arange(U), d.test_items, 99, np.random.default_rng(0))
+        assert cand.shape == (U, 100) and np.array_equal(cand[:, 0], d.test_items)
+        for u in range(U):
+            seen = set(d.indices[d.indptr[u]:d.indptr[u + 1]].tolist())
+            neg = cand[u, 1:1 + valid[u]].tolist()
+            assert len(set(neg)) == len(neg) and not (set(neg) & seen) and d.test_items[u] not in neg
+            assert valid[u] == min(99, N - len(seen) - 1)

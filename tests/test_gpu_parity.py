@@ -360,3 +360,34 @@ def test_cuda_graph_step_equals_eager(dev, precision):
         assert d0 == d1
     for k in s0:
         assert torch.equal(s0[k], s1[k]), k
+
+
+def test_negative_sampling_eval_matches_oracle(dev):
+    """99-negative protocol (src/ml/evaluate.py:149-215): same candidates -> same ranks as the oracle's scoring."""
+    import pandas as pd
+    from hvae_b200 import sampling
+    from hvae_b200.evaluate import RecommendationEvaluator
+    from oracle import hvae_oracle as orc
+    c = Case("tiny_two_hidden")
+    m = _build(c, dev, state="final")
+    o = orc.OracleVAE(**c.model_kwargs())
+    o.load_state_dict(c.state("final"))
+    o.eval()
+    u2i = {f"u{i:07d}": i for i in range(c.n_users)}
+    i2i = {f"i{i:07d}": i for i in range(c.n_items)}
+    ev = RecommendationEvaluator(m, c.csr, u2i, i2i, dev, batch_users=64)
+    users, tests = np.arange(c.n_users), c.test_items.astype(np.int64)
+    cand, valid = sampling.sample_negatives(c.csr.indptr, c.csr.indices, c.n_items, users, tests, 99, np.random.default_rng(5))
+    ranks = sampling.candidate_ranks(ev, users, cand)
+    flips = 0
+    for u in users:
+        s = orc.user_scores(o, c.csr, u)
+        ranked = orc.negative_sampling_rank(s, cand[u, 0], cand[u, 1:1 + valid[u]])
+        ref_rank = int(np.where(ranked == cand[u, 0])[0][0])
+        got = int(ranks[u]) - (99 - int(valid[u]))
+        flips += int(got != ref_rank)
+    assert flips <= max(1, c.n_users // 200)          # only exact-tie / last-ulp neighbours may swap
+    test_df = pd.DataFrame({"user_id": [f"u{i:07d}" for i in users], "asin": [f"i{int(t):07d}" for t in tests]})
+    res = ev.evaluate_dataset_with_negatives(test_df, 99, [5, 10], seed=5)
+    assert set(res) == {5, 10} and 0.0 <= res[10]["ndcg"] <= res[10]["hit_ratio"] <= 1.0
+    assert res[5]["hit_ratio"] <= res[10]["hit_ratio"]
