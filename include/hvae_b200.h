@@ -86,6 +86,13 @@ int hvae_batch_release(const int32_t* uniq_item, const int32_t* n_unique, int ca
 int hvae_gemm_f32(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
                   int64_t b_cs, float* C, int64_t ldc, const float* bias, float alpha, void* stream);
 
+/* Same contract on the tensor cores (tcgen05 kind::tf32: fp32 operands read as TF32, fp32 accumulation in TMEM); used
+ * for the MLP-stack GEMMs in bf16 mode.  Needs unit stride on one axis of A and of B, the other stride % 4 == 0 and
+ * 16-byte aligned bases: hvae_gemm_tf32_supported() returns 1 when that holds. */
+size_t hvae_gemm_tf32_supported(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs);
+int hvae_gemm_tf32(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                   int64_t b_cs, float* C, int64_t ldc, const float* bias, float alpha, void* stream);
+
 /* ---- latent (model.py:157-179, 92-93, 281-290) -------------------------------------------------------- */
 int hvae_reparam_kl(const float* ml, int ldml, const float* eps, int B, int L, float* z, int ldz, float* kl_row,
                     void* stream);
@@ -145,6 +152,11 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
 size_t hvae_tc_grad_splits(int B, int N, int d);
 int hvae_tc_score_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, float* Opart,
                        int ldo, void* stream);
+
+/* hvae_tc_score_lse + hvae_tc_score_grad as two launches (the backward kernel merges the forward's partial
+ * max / sum-exp itself and publishes lse). */
+int hvae_tc_score_lse_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* lse, float* workspace,
+                           float* Opart, int ldo, void* stream);
 
 /* ---- optimiser (train.py:63,88-92; model.py:312-323) --------------------------------------------------- */
 /* advance != 0: a training step (Adam step count, annealing step and the noise counter (+= noise_stride) move on) */

@@ -1,0 +1,293 @@
+// Small dense GEMMs of the MLP stack on the tensor cores (bf16/"tensor-core" mode of the model):
+//   C[m,n] = alpha * sum_k A(m,k) * B(k,n) (+ bias[n]),   fp32 operands read as TF32, fp32 accumulation in TMEM.
+// Same contract as hvae_gemm_f32 (arbitrary transposes through strides), so the engine swaps one for the other:
+// fc_mu/fc_logvar, the projection MLP and the deeper hidden layers, forward, dX and dW
+// (reference src/ml/model.py:90-95,114,126-127 and their autograd).  At a 512-user batch these nine GEMMs are
+// 400-600 wide and latency-bound; a TMA-fed tcgen05 tile (128 x 64, k-blocks of 32 floats = one 128B swizzle span)
+// turns each into a few microseconds.  The fp32 ("exact") mode keeps the FFMA kernel.
+// The MMA reads both operands K-major (128B-swizzled rows of 32 floats).  An operand whose m / n axis is the
+// contiguous one in memory (the transposed uses: dX = dY W, dW = dY^T X) is TMA-loaded un-swizzled into a staging
+// area and transposed smem -> smem by the four epilogue warps, which are idle during the main loop anyway
+// (kind::tf32 does not accept MN-major shared-memory descriptors in the 128B-swizzle form: measured, it yields zeros).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "hvae_b200.h"
+#include "tc_common.cuh"
+
+namespace hvae {
+namespace tc {
+
+constexpr int TG_BM = 128, TG_BN = 64, TG_BK = 32, TG_MAX_STAGES = 8;
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 4, TG_B_BYTES = TG_BN * TG_BK * 4, TG_TILES = TG_A_BYTES + TG_B_BYTES;
+// stage = [A tile | B tile | A raw (only if A is MN-major) | B raw (only if B is MN-major)]; as many stages as fit (<= 8)
+constexpr int TG_SMEM_BUDGET = 196608;
+constexpr int TG_CONV_WARPS = 8, TG_THREADS = 64 + 32 * TG_CONV_WARPS;
+
+struct TGemmParams {
+    int M, N, K;
+    int a_mn, b_mn;   // 1: operand is MN-major (m resp. n contiguous in memory)
+    int stage_bytes, n_stages;
+    int direct;       // debug (HVAE_TF32_TRUNC=1, both operands K-major): skip the rounding pass, the MMA truncates
+    float* C;
+    int64_t ldc;
+    const float* bias;
+    float alpha;
+};
+
+struct __align__(8) TGemmBarriers {
+    uint64_t raw_full[TG_MAX_STAGES], full[TG_MAX_STAGES], empty[TG_MAX_STAGES], acc_full;
+    uint32_t tmem_base;
+};
+
+// raw [32 k][32 x] fp32 boxes (x = m or n, one box per 32 x) -> K-major tile rows x: 32 k-floats = 128 B, 16-byte chunk c
+// stored at c ^ (x & 7) (the 128B swizzle the UMMA descriptor expects).  One thread per row x.
+// Values are rounded to TF32 with round-to-nearest on the way (the MMA itself truncates fp32 operands, which biases
+// every product low by ~2^-11: measured 1.5e-3 relative on the KL term).
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void transpose_to_kmajor(const uint8_t* raw, uint8_t* tile, int x) {
+    const float* src = reinterpret_cast<const float*>(raw + (x >> 5) * 4096) + (x & 31);
+    uint8_t* dst = tile + x * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 v;
+        v.x = rn_tf32(src[(4 * c + 0) * 32]); v.y = rn_tf32(src[(4 * c + 1) * 32]);
+        v.z = rn_tf32(src[(4 * c + 2) * 32]); v.w = rn_tf32(src[(4 * c + 3) * 32]);
+        *reinterpret_cast<float4*>(dst + ((c ^ (x & 7)) << 4)) = v;
+    }
+}
+// K-major operand already in place (TMA wrote it swizzled): round its row x in place.
+__device__ __forceinline__ void round_row_inplace(uint8_t* tile, int x) {
+    float4* row = reinterpret_cast<float4*>(tile + x * 128);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int cc = c ^ (x & 7);      // rows are 128 B apart: walk the chunks in swizzled order -> bank-conflict free
+        float4 v = row[cc];
+        v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w);
+        row[cc] = v;
+    }
+}
+
+// kind::tf32 instruction descriptor: D = f32, A = B = tf32 (format 2), major bits, N>>3, M>>4
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) | (uint32_t(N >> 3) << 17) |
+           (uint32_t(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, TGemmParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int TG_STAGES = P.n_stages, TG_STAGE = P.stage_bytes;
+    TGemmBarriers* bars = reinterpret_cast<TGemmBarriers*>(smem + TG_SMEM_BUDGET);
+    const int raw_a = TG_TILES, raw_b = TG_TILES + (P.a_mn ? TG_A_BYTES : 0);      // offsets of the raw areas in a stage
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
+    const int KB = (P.K + TG_BK - 1) / TG_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < TG_STAGES; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        mbar_init(&bars->acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TG_BN>(&bars->tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % TG_STAGES;
+                mbar_wait(&bars->empty[s], ((kb / TG_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&bars->raw_full[s], TG_TILES);
+                uint8_t* a = smem + s * TG_STAGE;
+                uint8_t* b = a + TG_A_BYTES;
+                if (!P.a_mn) {
+                    tma_load_2d(a, &tmA, kb * TG_BK, m0, &bars->raw_full[s]);             // box {32 k, 128 m}, swizzled, final place
+                } else {
+                    for (int g = 0; g < TG_BM / 32; ++g)                                  // raw boxes {32 m, 32 k}
+                        tma_load_2d(a + raw_a + g * 4096, &tmA, m0 + g * 32, kb * TG_BK, &bars->raw_full[s]);
+                }
+                if (!P.b_mn) {
+                    tma_load_2d(b, &tmB, kb * TG_BK, n0, &bars->raw_full[s]);             // box {32 k, 64 n}
+                } else {
+                    for (int g = 0; g < TG_BN / 32; ++g)                                  // raw boxes {32 n, 32 k}
+                        tma_load_2d(a + raw_b + g * 4096, &tmB, n0 + g * 32, kb * TG_BK, &bars->raw_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(TG_BM, TG_BN, 0, 0);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % TG_STAGES;
+                mbar_wait(P.direct ? &bars->raw_full[s] : &bars->full[s], (kb / TG_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * TG_STAGE), b0 = a0 + TG_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < TG_BK / 8; ++k)        // one MMA = 8 tf32 (32 B) along K; rows of 128 B, 8-row groups 1024 B apart
+                    umma_tf32(tmem_base, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc, (kb | k) != 0);
+                umma_commit(&bars->empty[s]);
+            }
+            umma_commit(&bars->acc_full);
+        }
+    } else {
+        // Main loop: the eight conversion warps each own every 8th k-block (their fence + barrier round trips overlap):
+        // round (and, for MN-major operands, transpose) the whole stage into K-major TF32 tiles, lane <-> rows lane+32i.
+        // (as many conversion warps as stages take part, so a stage is always served by the same warp: a parity wait
+        // on a barrier that is a whole phase behind would otherwise pass immediately)
+        const int cw = warp - 2;
+        for (int kb = cw; kb < KB && cw < TG_STAGES && !P.direct; kb += TG_STAGES) {
+            const int s = kb % TG_STAGES;
+            mbar_wait(&bars->raw_full[s], (kb / TG_STAGES) & 1);
+            uint8_t* a = smem + s * TG_STAGE;
+#pragma unroll
+            for (int i = 0; i < TG_BM / 32; ++i) {
+                const int x = lane + 32 * i;
+                if (P.a_mn) transpose_to_kmajor(a + raw_a, a, x);
+                else round_row_inplace(a, x);
+            }
+#pragma unroll
+            for (int i = 0; i < TG_BN / 32; ++i) {
+                const int x = lane + 32 * i;
+                if (P.b_mn) transpose_to_kmajor(a + raw_b, a + TG_A_BYTES, x);
+                else round_row_inplace(a + TG_A_BYTES, x);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->full[s]);
+        }
+        if (warp < 6) {                 // the epilogue needs only four warps (one per TMEM lane quarter)
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        mbar_wait(&bars->acc_full, 0);
+        tc_fence_after();
+        const bool vec = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+#pragma unroll 1
+        for (int c = 0; c < TG_BN / 32; ++c) {
+            float v[32];
+            tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + c * 32, v);
+            tmem_ld_wait();
+            if (m >= P.M) continue;
+            const int nb = n0 + c * 32;
+            float* crow = P.C + (int64_t)m * P.ldc + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int n = nb + j + e;
+                    o[e] = v[j + e] * P.alpha + ((P.bias && n < P.N) ? P.bias[n] : 0.f);
+                }
+                if (vec && nb + j + 3 < P.N) {
+                    *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (nb + j + e < P.N) crow[j + e] = o[e];
+                }
+            }
+        }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TG_BN>(tmem_base);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp32 2-D view [outer, inner] (inner contiguous, outer stride `ld` floats); box = {32 inner, box_outer}; 128B swizzle
+static int make_tmap_f32(CUtensorMap* out, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_outer, bool swizzle) {
+    static EncodeTiledFn2 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn2>(p);
+        if (!fn) return hvae_fail("cuTensorMapEncodeTiled is not available from the driver");
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return hvae_fail("cuTensorMapEncodeTiled(f32) failed (%d) inner=%lld outer=%lld ld=%lld", (int)r, (long long)inner,
+                                            (long long)outer, (long long)ld);
+    return 0;
+}
+
+constexpr size_t kTGemmSmem = TG_SMEM_BUDGET + 512 + 1024;
+
+}  // namespace tc
+}  // namespace hvae
+
+using namespace hvae;
+using namespace hvae::tc;
+
+extern "C" {
+
+// 1 if the operands satisfy the TMA constraints of hvae_gemm_tf32 (unit stride on one axis of A and of B, the
+// other stride a multiple of 4 floats, 16-byte aligned bases), else 0.
+size_t hvae_gemm_tf32_supported(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs) {
+    const bool a_ok = (a_cs == 1 && a_rs % 4 == 0) || (a_rs == 1 && a_cs % 4 == 0);
+    const bool b_ok = (b_rs == 1 && b_cs % 4 == 0) || (b_cs == 1 && b_rs % 4 == 0);
+    return (a_ok && b_ok && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0) ? 1 : 0;
+}
+
+int hvae_gemm_tf32(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
+                   float* C, int64_t ldc, const float* bias, float alpha, void* stream) {
+    if (M == 0 || N == 0) return 0;
+    HVAE_REQUIRE(K > 0, "gemm_tf32: K must be positive");
+    HVAE_REQUIRE(hvae_gemm_tf32_supported(A, a_rs, a_cs, B, b_rs, b_cs), "gemm_tf32: operand strides/alignment not TMA-compatible");
+    TGemmParams P{};
+    P.M = M; P.N = N; P.K = K; P.C = C; P.ldc = ldc; P.bias = bias; P.alpha = alpha;
+    P.a_mn = (a_cs == 1) ? 0 : 1;
+    P.b_mn = (b_rs == 1) ? 0 : 1;
+    if (a_cs == 1 && a_rs == 1) P.a_mn = 0;
+    if (b_rs == 1 && b_cs == 1) P.b_mn = 0;
+    P.stage_bytes = TG_TILES + (P.a_mn ? TG_A_BYTES : 0) + (P.b_mn ? TG_B_BYTES : 0);
+    P.n_stages = min(TG_MAX_STAGES, TG_SMEM_BUDGET / P.stage_bytes);
+    static const bool trunc = getenv("HVAE_TF32_TRUNC") != nullptr;
+    P.direct = (trunc && !P.a_mn && !P.b_mn) ? 1 : 0;
+    CUtensorMap tmA, tmB;
+    // A(m,k): K-major -> view [M outer, K inner] stride a_rs; MN-major -> view [K outer, M inner] stride a_cs
+    if (int rc = P.a_mn ? make_tmap_f32(&tmA, A, M, K, a_cs, 32, false) : make_tmap_f32(&tmA, A, K, M, a_rs, TG_BM, true)) return rc;
+    // B(k,n): K-major (k contiguous) -> view [N outer, K inner] stride b_cs; MN-major -> view [K outer, N inner] stride b_rs
+    if (int rc = P.b_mn ? make_tmap_f32(&tmB, B, N, K, b_rs, 32, false) : make_tmap_f32(&tmB, B, K, N, b_cs, TG_BN, true)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HVAE_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTGemmSmem));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(N, TG_BN), ceil_div(M, TG_BM));
+    gemm_tf32_kernel<<<grid, TG_THREADS, kTGemmSmem, (cudaStream_t)stream>>>(tmA, tmB, P);
+    HVAE_LAUNCH_CHECK("gemm_tf32");
+    return 0;
+}
+
+}  // extern "C"

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + STAGES * STAGE_BYTES);
     float* list_v = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);           // [128][K]   (TOPK)
-    int* list_i = reinterpret_cast<int*>(list_v + BM * MAXK_TC);
+    int* list_i = reinterpret_cast<int*>(list_v + BM * (MAXK_TC + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, split = blockIdx.y;
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
         // top-K state
         float thr_v = -INFINITY;
         int thr_i = -1, thr_pos = 0, cnt = 0;
-        float* lv = list_v + r_local * MAXK_TC;
-        int* li = list_i + r_local * MAXK_TC;
+        float* lv = list_v + r_local * (MAXK_TC + 1);
+        int* li = list_i + r_local * (MAXK_TC + 1);
         int64_t seen_p = 0, seen_e = 0;
         int next_seen = INT_MAX;
         if (MODE == MODE_TOPK) {
@@ -182,34 +182,45 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
                     l_run = l_run * exp2f((m_run - m_new) * kLog2e) + s;
                     m_run = m_new;
                 } else {
+                    // candidate bits first (32 compares), then a compact loop over the few set bits: the insertion
+                    // code exists once, not 32 times (instruction-cache footprint), and v[j] is fetched by selects
+                    unsigned mbits = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = v[j];
-                        if (x >= thr_v && c * 32 + j < n_valid) {
-                            const int lc = c * 32 + j, gi = P.item_offset + col0 + lc;
-                            bool ok = cnt < P.K || better(x, gi, thr_v, thr_i);
-                            if (ok && nmask) {
-                                if (nmask <= 16) {
-                                    for (int e = 0; e < nmask; ++e) ok &= (mcol[e] != lc);
-                                } else {  // rare: many seen items in one tile -> exact binary search in the row's CSR slice
-                                    const int u = P.rows ? P.rows[row] : row;
-                                    int64_t lo = P.indptr[u], hi = P.indptr[u + 1];
-                                    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (P.indices[mid] < gi) lo = mid + 1; else hi = mid; }
-                                    ok = !(lo < P.indptr[u + 1] && P.indices[lo] == gi);
-                                }
+                    for (int j = 0; j < 32; ++j) mbits |= (v[j] >= thr_v) ? (1u << j) : 0u;
+                    const int left = n_valid - c * 32;
+                    if (left < 32) mbits &= (1u << left) - 1u;
+                    if (!row_ok) mbits = 0;
+                    while (mbits) {
+                        const int j = __ffs(mbits) - 1;
+                        mbits &= mbits - 1;
+                        float x = v[0];
+#pragma unroll
+                        for (int t = 1; t < 32; ++t) x = (t == j) ? v[t] : x;
+                        const int lc = c * 32 + j, gi = P.item_offset + col0 + lc;
+                        if (cnt == P.K && !better(x, gi, thr_v, thr_i)) continue;
+                        if (nmask) {
+                            bool seen = false;
+                            if (nmask <= 16) {
+                                for (int e = 0; e < nmask; ++e) seen |= (mcol[e] == lc);
+                            } else {  // rare: many seen items in one tile -> exact binary search in the row's CSR slice
+                                const int u = P.rows ? P.rows[row] : row;
+                                int64_t lo = P.indptr[u], hi = P.indptr[u + 1];
+                                while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (P.indices[mid] < gi) lo = mid + 1; else hi = mid; }
+                                seen = lo < P.indptr[u + 1] && P.indices[lo] == gi;
                             }
-                            if (ok && row_ok) {
-                                int pos = thr_pos;
-                                if (cnt < P.K) pos = cnt++;
-                                lv[pos] = x;
-                                li[pos] = gi;
-                                if (cnt == P.K) {  // recompute the list's worst element (= threshold)
-                                    float wv = lv[0]; int wi = li[0], wp = 0;
-                                    for (int e = 1; e < P.K; ++e)
-                                        if (better(wv, wi, lv[e], li[e])) { wv = lv[e]; wi = li[e]; wp = e; }
-                                    thr_v = wv; thr_i = wi; thr_pos = wp;
-                                }
+                            if (seen) continue;
+                        }
+                        int pos = thr_pos;
+                        if (cnt < P.K) pos = cnt++;
+                        lv[pos] = x;
+                        li[pos] = gi;
+                        if (cnt == P.K) {  // recompute the list's worst element (= threshold)
+                            float wv = lv[0]; int wi = li[0], wp = 0;
+                            for (int e = 1; e < P.K; ++e) {
+                                const float ev = lv[e]; const int ei = li[e];
+                                if (better(wv, wi, ev, ei)) { wv = ev; wi = ei; wp = e; }
                             }
+                            thr_v = wv; thr_i = wi; thr_pos = wp;
                         }
                     }
                 }
@@ -273,7 +284,11 @@ constexpr int G_PBYTES = 32768;               // P tile [128 users x 128 items] 
 struct GradParams {
     int B, N, d;
     int tiles_per_split, n_splits;
-    const float* lse;     // [B]
+    const float* lse;     // [B], or null: merge the forward kernel's partials below (and publish lse_out)
+    const float* part_m;  // [B, lse_splits] per-split running max / sum-exp of score_stats_kernel<LSE>
+    const float* part_l;
+    int lse_splits;
+    float* lse_out;       // [B]
     float* Opart;         // [n_splits][B][ldo]
     int ldo;
 };
@@ -399,7 +414,22 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
         const int r_local = q * 32 + lane;
         const int row = m_tile * BM + r_local;
         const bool row_ok = row < P.B;
-        const float lse2 = row_ok ? P.lse[row] * kLog2e : 0.f;
+        float lse_row = 0.f;
+        if (row_ok) {
+            if (P.lse) {
+                lse_row = P.lse[row];
+            } else {   // merge the forward partials here instead of in a separate launch
+                const float* pm = P.part_m + (size_t)row * P.lse_splits;
+                const float* pl = P.part_l + (size_t)row * P.lse_splits;
+                float M = -INFINITY;
+                for (int sp = 0; sp < P.lse_splits; ++sp) M = fmaxf(M, pm[sp]);
+                float l = 0.f;
+                for (int sp = 0; sp < P.lse_splits; ++sp) l += pl[sp] * expf(pm[sp] - M);
+                lse_row = M + logf(l);
+                if (chunk == 0 && split == 0) P.lse_out[row] = lse_row;
+            }
+        }
+        const float lse2 = lse_row * kLog2e;
         const uint32_t lane_base = uint32_t(q * 32) << 16;
         for (int ti = 0; ti < T; ++ti) {
             const int pb = ti & 1;
@@ -516,7 +546,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int l
 
 static int pick_splits(int m_tiles, int n_tiles) { return pick_wave_splits(m_tiles, n_tiles); }
 
-constexpr size_t kStatsSmem = STAGES * STAGE_BYTES + 256 + BM * MAXK_TC * 8 + 1024;
+constexpr size_t kStatsSmem = STAGES * STAGE_BYTES + 256 + BM * (MAXK_TC + 1) * 8 + 1024;
 
 }  // namespace tc
 }  // namespace hvae
@@ -536,10 +566,8 @@ int hvae_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, 
 
 size_t hvae_tc_n_splits(int B, int N) { return (size_t)pick_splits(ceil_div(B, BM), ceil_div(N, BN)); }
 
-// workspace: 2 * B * n_splits floats
-int hvae_tc_score_lse(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* lse, float* workspace, void* stream) {
-    if (B == 0) return 0;
-    HVAE_REQUIRE(N > 0 && d > 0, "tc_score_lse: empty catalogue");
+static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* workspace, int* n_splits,
+                            cudaStream_t stream) {
     CUtensorMap tmU, tmE;
     if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
     if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, BN)) return rc;
@@ -553,14 +581,55 @@ int hvae_tc_score_lse(const void* U, int ldu, int B, const void* E, int lde, int
     static bool attr_set = false;
     if (!attr_set) {
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
-        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
         attr_set = true;
     }
-    score_stats_kernel<MODE_LSE><<<dim3(m_tiles, P.n_splits), 192, kStatsSmem, (cudaStream_t)stream>>>(tmU, tmE, P);
+    score_stats_kernel<MODE_LSE><<<dim3(m_tiles, P.n_splits), 192, kStatsSmem, stream>>>(tmU, tmE, P);
     HVAE_LAUNCH_CHECK("tc_score_lse");
-    lse_merge_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(P.part_m, P.part_l, B, P.n_splits, lse);
+    *n_splits = P.n_splits;
+    return 0;
+}
+
+static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, const float* part_m,
+                       const float* part_l, int lse_splits, float* lse_out, float* Opart, int ldo, cudaStream_t stream) {
+    HVAE_REQUIRE(ldo % 4 == 0 && ldo >= d, "tc_score_grad: bad ldo=%d for d=%d", ldo, d);
+    CUtensorMap tmU, tmE;
+    if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
+    if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, 64)) return rc;
+    const int m_tiles = ceil_div(B, BM), n_chunks = ceil_div(round_up(d, BK), G_DCHUNK), n_tiles = ceil_div(N, G_BN);
+    GradParams P{};
+    P.B = B; P.N = N; P.d = d; P.lse = lse; P.part_m = part_m; P.part_l = part_l; P.lse_splits = lse_splits; P.lse_out = lse_out;
+    P.Opart = Opart; P.ldo = ldo;
+    P.n_splits = pick_grad_splits(m_tiles, n_chunks, n_tiles);
+    P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
+    static bool attr_set = false;
+    if (!attr_set) {
+        HVAE_CUDA(cudaFuncSetAttribute(score_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
+        attr_set = true;
+    }
+    score_grad_kernel<<<dim3(m_tiles, n_chunks, P.n_splits), 192, kGradSmem, stream>>>(tmU, tmE, P);
+    HVAE_LAUNCH_CHECK("tc_score_grad");
+    return 0;
+}
+
+// workspace: 2 * B * n_splits floats
+int hvae_tc_score_lse(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* lse, float* workspace, void* stream) {
+    if (B == 0) return 0;
+    HVAE_REQUIRE(N > 0 && d > 0, "tc_score_lse: empty catalogue");
+    int ns = 0;
+    if (int rc = launch_stats_lse(U, ldu, B, E, lde, N, d, workspace, &ns, (cudaStream_t)stream)) return rc;
+    lse_merge_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(workspace, workspace + (size_t)B * ns, B, ns, lse);
     HVAE_LAUNCH_CHECK("tc_score_lse merge");
     return 0;
+}
+
+// Forward + backward through the scores in two launches: the backward kernel merges the forward partials itself.
+int hvae_tc_score_lse_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* lse, float* workspace,
+                           float* Opart, int ldo, void* stream) {
+    if (B == 0) return 0;
+    HVAE_REQUIRE(N > 0 && d > 0, "tc_score_lse_grad: empty catalogue");
+    int ns = 0;
+    if (int rc = launch_stats_lse(U, ldu, B, E, lde, N, d, workspace, &ns, (cudaStream_t)stream)) return rc;
+    return launch_grad(U, ldu, B, E, lde, N, d, nullptr, workspace, workspace + (size_t)B * ns, ns, lse, Opart, ldo, (cudaStream_t)stream);
 }
 
 // Top-K over the N items of E (global ids item_offset..item_offset+N).  cand_val / cand_idx: [B, n_splits*K] scratch;
@@ -599,23 +668,7 @@ size_t hvae_tc_grad_splits(int B, int N, int d) {
 int hvae_tc_score_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, float* Opart, int ldo,
                        void* stream) {
     if (B == 0) return 0;
-    HVAE_REQUIRE(ldo % 4 == 0 && ldo >= d, "tc_score_grad: bad ldo=%d for d=%d", ldo, d);
-    CUtensorMap tmU, tmE;
-    if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
-    if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, 64)) return rc;
-    const int m_tiles = ceil_div(B, BM), n_chunks = ceil_div(round_up(d, BK), G_DCHUNK), n_tiles = ceil_div(N, G_BN);
-    GradParams P{};
-    P.B = B; P.N = N; P.d = d; P.lse = lse; P.Opart = Opart; P.ldo = ldo;
-    P.n_splits = pick_grad_splits(m_tiles, n_chunks, n_tiles);
-    P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
-    static bool attr_set = false;
-    if (!attr_set) {
-        HVAE_CUDA(cudaFuncSetAttribute(score_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
-        attr_set = true;
-    }
-    score_grad_kernel<<<dim3(m_tiles, n_chunks, P.n_splits), 192, kGradSmem, (cudaStream_t)stream>>>(tmU, tmE, P);
-    HVAE_LAUNCH_CHECK("tc_score_grad");
-    return 0;
+    return launch_grad(U, ldu, B, E, lde, N, d, lse, nullptr, nullptr, 0, nullptr, Opart, ldo, (cudaStream_t)stream);
 }
 
 }  // extern "C"

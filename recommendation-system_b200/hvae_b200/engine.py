@@ -316,7 +316,15 @@ class Engine:
             self.slot_of_item = torch.full((self.lay.N,), -1, dtype=torch.int32, device=self.dev)
 
     def gemm(self, M, N, K, A, a_rs, a_cs, Bp, b_rs, b_cs, C, ldc, bias=None, alpha=1.0):
+        """fp32 FFMA GEMM (exact mode; materialised scores in either mode)."""
         self.lib.gemm_f32(M, N, K, A, a_rs, a_cs, Bp, b_rs, b_cs, C, ldc, bias, alpha, self.stream)
+
+    def mm(self, M, N, K, A, a_rs, a_cs, Bp, b_rs, b_cs, C, ldc, bias=None, alpha=1.0):
+        """GEMM of the MLP stack: tensor cores (TF32 operands, fp32 accumulation) in bf16 mode, FFMA in fp32 mode."""
+        if self.precision != "fp32" and self.lib.gemm_tf32_supported(A, a_rs, a_cs, Bp, b_rs, b_cs):
+            self.lib.gemm_tf32(M, N, K, A, a_rs, a_cs, Bp, b_rs, b_cs, C, ldc, bias, alpha, self.stream)
+        else:
+            self.lib.gemm_f32(M, N, K, A, a_rs, a_cs, Bp, b_rs, b_cs, C, ldc, bias, alpha, self.stream)
 
     # -- forward ---------------------------------------------------------------------------------------------
     def encode(self, batch: Batch, masks=None, keep=True):
@@ -338,7 +346,7 @@ class Engine:
                                       p(mask), self.keep_scale, p(pre), p(mean), p(rstd), p(act), st)
             else:
                 w = lay.slots[f"encoder.{4 * i}.weight"]
-                self.gemm(B, hi, h[i - 1], p(acts[-1]), r4(h[i - 1]), 1, self.P(f"encoder.{4 * i}.weight"), 1, w.ld,
+                self.mm(B, hi, h[i - 1], p(acts[-1]), r4(h[i - 1]), 1, self.P(f"encoder.{4 * i}.weight"), 1, w.ld,
                           p(pre), ld, self.P(f"encoder.{4 * i}.bias"))
                 lib.ln_act_fwd(p(pre), B, hi, ld, self.P(f"encoder.{4 * i + 1}.weight"), self.P(f"encoder.{4 * i + 1}.bias"),
                                p(mask), self.keep_scale, p(mean), p(rstd), p(act), st)
@@ -347,7 +355,7 @@ class Engine:
         ldml = r4(2 * L)
         ml = ws.get("ml", (B, ldml))
         wm = lay.slots["fc_mu.weight"]
-        self.gemm(B, 2 * L, h[-1], p(acts[-1]), r4(h[-1]), 1, self.P("fc_mu.weight"), 1, wm.ld, p(ml), ldml, self.P("fc_ml.bias"))
+        self.mm(B, 2 * L, h[-1], p(acts[-1]), r4(h[-1]), 1, self.P("fc_mu.weight"), 1, wm.ld, p(ml), ldml, self.P("fc_ml.bias"))
         return ml
 
     def latent_and_project(self, B, ml, eps=None, pmask=None, want_kl=True):
@@ -362,9 +370,9 @@ class Engine:
             return z
         q, t, u = ws.get("q", (B, ldd)), ws.get("t", (B, ldd)), ws.get("u", (B, ldd))
         w0, w3 = lay.slots["projection_layer.0.weight"], lay.slots["projection_layer.3.weight"]
-        self.gemm(B, d, L, p(z), ldz, 1, self.P("projection_layer.0.weight"), 1, w0.ld, p(q), ldd, self.P("projection_layer.0.bias"))
+        self.mm(B, d, L, p(z), ldz, 1, self.P("projection_layer.0.weight"), 1, w0.ld, p(q), ldd, self.P("projection_layer.0.bias"))
         lib.gelu_drop_fwd(p(q), p(pmask), self.keep_scale, B, d, ldd, p(t), st)
-        self.gemm(B, d, d, p(t), ldd, 1, self.P("projection_layer.3.weight"), 1, w3.ld, p(u), ldd, self.P("projection_layer.3.bias"))
+        self.mm(B, d, d, p(t), ldd, 1, self.P("projection_layer.3.weight"), 1, w3.ld, p(u), ldd, self.P("projection_layer.3.bias"))
         return u
 
     def scores_dense(self, u, B, out=None):
@@ -450,19 +458,19 @@ class Engine:
             w0, w3 = lay.slots["projection_layer.0.weight"], lay.slots["projection_layer.3.weight"]
             # dWp3 = dU^T t ; dbp3 = colsum(dU) ; dt = dU Wp3   (three independent kernels: side streams 0/1 + main)
             with self.side(0):
-                self.gemm(d, d, B, p(dU), 1, ldd, p(t), ldd, 1, self.G("projection_layer.3.weight"), w3.ld)
+                self.mm(d, d, B, p(dU), 1, ldd, p(t), ldd, 1, self.G("projection_layer.3.weight"), w3.ld)
             with self.side(1):
                 lib.colsum(p(dU), ldd, B, d, self.G("projection_layer.3.bias"), p(cs_ws), self.stream)
             dt = ws.get("dt", (B, ldd))
-            self.gemm(B, d, d, p(dU), ldd, 1, self.P("projection_layer.3.weight"), w3.ld, 1, p(dt), ldd)
+            self.mm(B, d, d, p(dU), ldd, 1, self.P("projection_layer.3.weight"), w3.ld, 1, p(dt), ldd)
             dq = ws.get("dq", (B, ldd))
             lib.gelu_drop_bwd(p(dt), p(q), p(pmask), self.keep_scale, B, d, ldd, p(dq), st)
             with self.side(0):
-                self.gemm(d, L, B, p(dq), 1, ldd, p(z), ldz, 1, self.G("projection_layer.0.weight"), w0.ld)
+                self.mm(d, L, B, p(dq), 1, ldd, p(z), ldz, 1, self.G("projection_layer.0.weight"), w0.ld)
             with self.side(1):
                 lib.colsum(p(dq), ldd, B, d, self.G("projection_layer.0.bias"), p(cs_ws2), self.stream)
             dz = ws.get("dz", (B, ldz))
-            self.gemm(B, L, d, p(dq), ldd, 1, self.P("projection_layer.0.weight"), w0.ld, 1, p(dz), ldz)
+            self.mm(B, L, d, p(dq), ldd, 1, self.P("projection_layer.0.weight"), w0.ld, 1, p(dz), ldz)
         dml = ws.get("dml", (B, ldml))
         lib.latent_bwd(p(dz), ldz, p(ml), ldml, p(eps), B, L, self.state_ptr("kl_coef") if ext_dml is None else p(self._zero()),
                        p(dml), st)
@@ -472,11 +480,11 @@ class Engine:
         nh = len(h)
         act_last = ws.get(f"act{nh - 1}", (B, r4(h[-1])))
         with self.side(0):
-            self.gemm(2 * L, h[-1], B, p(dml), 1, ldml, p(act_last), r4(h[-1]), 1, self.G("fc_mu.weight"), wm.ld)
+            self.mm(2 * L, h[-1], B, p(dml), 1, ldml, p(act_last), r4(h[-1]), 1, self.G("fc_mu.weight"), wm.ld)
         with self.side(1):
             lib.colsum(p(dml), ldml, B, 2 * L, self.G("fc_ml.bias"), p(cs_ws), self.stream)
         dact = ws.get(f"dact{nh - 1}", (B, r4(h[-1])))
-        self.gemm(B, h[-1], 2 * L, p(dml), ldml, 1, self.P("fc_mu.weight"), wm.ld, 1, p(dact), r4(h[-1]))
+        self.mm(B, h[-1], 2 * L, p(dml), ldml, 1, self.P("fc_mu.weight"), wm.ld, 1, p(dact), r4(h[-1]))
         ln_ws = ws.get("ln_ws", (max(lib.ln_bwd_workspace_floats(B, r4(hh)) for hh in h),))
         for i in range(nh - 1, -1, -1):
             hi, ld = h[i], r4(h[i])
@@ -490,9 +498,9 @@ class Engine:
                 w = lay.slots[f"encoder.{4 * i}.weight"]
                 prev = ws.get(f"act{i - 1}", (B, r4(h[i - 1])))
                 with self.side(0):
-                    self.gemm(hi, h[i - 1], B, p(dact), 1, ld, p(prev), r4(h[i - 1]), 1, self.G(f"encoder.{4 * i}.weight"), w.ld)
+                    self.mm(hi, h[i - 1], B, p(dact), 1, ld, p(prev), r4(h[i - 1]), 1, self.G(f"encoder.{4 * i}.weight"), w.ld)
                 dprev = ws.get(f"dact{i - 1}", (B, r4(h[i - 1])))
-                self.gemm(B, h[i - 1], hi, p(dact), ld, 1, self.P(f"encoder.{4 * i}.weight"), w.ld, 1, p(dprev), r4(h[i - 1]))
+                self.mm(B, h[i - 1], hi, p(dact), ld, 1, self.P(f"encoder.{4 * i}.weight"), w.ld, 1, p(dprev), r4(h[i - 1]))
                 dact = dprev
         self.dpre0 = dact
         if dense_w1 is not None:

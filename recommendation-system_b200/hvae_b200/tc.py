@@ -37,9 +37,14 @@ def score_loss_bf16(eng, batch, u, want_grad):
                             p(dot), p(xsum), eng.stream)
     ns = int(lib.tc_n_splits(B, N))
     wsl = ws.get("tc_lse_ws", (2 * B * ns,))
+    O = None
+    if want_grad and eng.prof is None:        # two launches: the backward kernel merges the forward partials itself
+        gs = int(lib.tc_grad_splits(B, N, d))
+        O = ws.get("tc_O", (gs, B, ldd))
+        lib.tc_score_lse_grad(p(ub), ld8, B, p(Eb), ld8, N, d, p(lse), p(wsl), p(O), ldd, st)
+        return lse, dot, xsum, O, xsum
     with eng.span("score_fwd"):
         lib.tc_score_lse(p(ub), ld8, B, p(Eb), ld8, N, d, p(lse), p(wsl), st)
-    O = None
     if want_grad:
         gs = int(lib.tc_grad_splits(B, N, d))
         O = ws.get("tc_O", (gs, B, ldd))

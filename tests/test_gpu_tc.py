@@ -121,3 +121,37 @@ def test_tc_grad_matches_torch(dev, B, N, d):
     assert torch.isfinite(O).all()
     assert float((O - ref_b).abs().max()) < 2e-3 * scale + 1e-6      # same rounding point: only exp ulps / order differ
     assert float((O - ref).abs().max()) < 1e-2 * scale + 1e-6        # against exact softmax: bf16 rounding of P
+
+
+def test_gemm_tf32_all_layouts(dev):
+    """tcgen05 kind::tf32 GEMM: every transpose combination the MLP forward/backward uses, ragged sizes, bias, alpha."""
+    from hvae_b200 import _cabi
+    lib = _cabi.lib()
+    g = torch.Generator().manual_seed(1)
+    st = torch.cuda.current_stream().cuda_stream
+    r4 = lambda n: (n + 3) // 4 * 4
+    for (M, N, K) in [(512, 400, 600), (130, 70, 33), (512, 384, 200), (400, 600, 512), (5, 8, 7), (257, 768, 200), (37, 22, 64)]:
+        A, B = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g)
+        bias = torch.randn(N, generator=g)
+        ref = (2.0 * (A.double() @ B.double()) + bias.double()).numpy()
+        scale = np.abs(ref).max()
+        for a_t in (False, True):
+            for b_t in (False, True):
+                # pad the leading dimensions to multiples of 4 floats as the engine's buffers are
+                if a_t:
+                    Ad = torch.zeros(K, r4(M)); Ad[:, :M] = A.t(); a_rs, a_cs = 1, r4(M)
+                else:
+                    Ad = torch.zeros(M, r4(K)); Ad[:, :K] = A; a_rs, a_cs = r4(K), 1
+                if b_t:
+                    Bd = torch.zeros(N, r4(K)); Bd[:, :K] = B.t(); b_rs, b_cs = 1, r4(K)
+                else:
+                    Bd = torch.zeros(K, r4(N)); Bd[:, :N] = B; b_rs, b_cs = r4(N), 1
+                Ad, Bd = Ad.to(dev), Bd.to(dev)
+                assert lib.gemm_tf32_supported(Ad.data_ptr(), a_rs, a_cs, Bd.data_ptr(), b_rs, b_cs) == 1
+                ldc = r4(N)
+                C = torch.full((M, ldc), float("nan"), device=dev)
+                lib.gemm_tf32(M, N, K, Ad.data_ptr(), a_rs, a_cs, Bd.data_ptr(), b_rs, b_cs, C.data_ptr(), ldc, bias.to(dev).data_ptr(), 2.0, st)
+                got = C[:, :N].cpu().numpy()
+                assert np.isfinite(got).all(), (M, N, K, a_t, b_t)
+                assert np.abs(got - ref).max() < 2e-3 * scale, (M, N, K, a_t, b_t, np.abs(got - ref).max(), scale)   # TF32: 10-bit mantissa
+                assert torch.isnan(C[:, N:]).all()        # pad columns untouched
