@@ -298,7 +298,7 @@ def main():
     if "score_bwd" in span_avg:
         kernels["score_bwd"] = {"ms": span_avg["score_bwd"], "bound": "tensor", "achieved": flops_fwd / (span_avg["score_bwd"] * 1e-3) / 1e12,
                                 "peak": pk["tc_sustained"], "unit": "TFLOP/s", "algorithmic_flops": flops_fwd,
-                                "executed_flops": 2 * flops_fwd}
+                                "executed_flops": flops_fwd * (1 + -(-((d + 63) // 64 * 64) // 384))}
     if "gather" in span_avg:
         nnz_avg = float(lens[order[:Bg * min(4, n_batches)]].sum()) / min(4, n_batches) / world
         gbytes = nnz_avg * (ld1 * 4 + 4) + B * (3 * ld1 * 4 + 16)
@@ -387,8 +387,7 @@ def main():
         model.train()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dist, dev)
         return
 
     cpu = None
@@ -404,10 +403,19 @@ def main():
             "config": workload_config(args.workload, c, world, args.precision),
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
             "value_hot_l2": K * Bg / (ms_hot * 1e-3), "ms_per_step_hot_l2": ms_hot / K,
-            "kernels": kernels, "spans_ms": span_avg, "eval": ev_out, "cuda_graph": bool(trainer.use_cuda_graph and world == 1)}
+            "kernels": kernels, "spans_ms": span_avg, "eval": ev_out, "cuda_graph": bool(trainer.use_cuda_graph)}
     print(json.dumps(line), flush=True)
+    _finish(world, dist, dev)
+
+
+def _finish(world, dist, dev):
+    """Multi-rank exit: the captured step graphs hold NCCL work, so synchronise and leave without tearing the communicator down
+    (process exit releases it; destroy_process_group() can wait forever on graph-captured collectives)."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

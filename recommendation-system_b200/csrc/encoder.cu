@@ -352,21 +352,80 @@ __global__ void colsum_chunk_kernel(const float* __restrict__ X, int ld, int R, 
     out[(size_t)blockIdx.y * out_ld + c] = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
 }
 
-// One CTA (4 warps) per touched item: grad row = sum over the item's (user, value) entries of
-// value * dH[user, :].  Entries were sorted stably by item, so the order -- hence the fp32 sum -- is fixed:
-// warp w sums entries w, w+4, ... in order, the four warp sums are combined as (0+1)+(2+3).
-// Entry ids are fetched 32 at a time (one per lane) and broadcast, every row is read as NCHUNK 16-byte
-// vectors per lane with two rows in flight.
+// Layer-1 weight gradient.  A touched item's gradient row = sum over its (user, value) entries of value * dH[user, :].
+// Item popularity is heavy-tailed (the top item of a Zipf catalogue sits in most rows of a batch), so the work is cut
+// into items of at most kW1Chunk entries (hvae_w1_plan, run beside the forward pass): one CTA (4 warps) per work item.
+// Entries were sorted stably by item, so every sum has a fixed order: warp w adds entries w, w+4, ... of its chunk, the
+// four warp sums combine as (0+1)+(2+3); an item with several chunks gets its partial rows added in chunk order by
+// w1_combine_kernel.  Entry ids are fetched 32 at a time (one per lane) and broadcast, every row is read as NCHUNK
+// 16-byte vectors per lane with two rows in flight.
+constexpr int kW1Chunk = 64;
+
+// Single CTA: chunk_base[s] = first work item of slot s, part_base[s] = first partial row of slot s (slots with one chunk
+// have none), n_work = chunk_base[n_unique].
+__global__ void __launch_bounds__(1024) w1_plan_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_unique,
+                                                        int32_t* __restrict__ chunk_base, int32_t* __restrict__ part_base,
+                                                        int32_t* __restrict__ n_work) {
+    __shared__ int wsum_a[32], wsum_b[32];
+    __shared__ int carry_a, carry_b;
+    const int n = *n_unique, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { carry_a = 0; carry_b = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int sl = base + threadIdx.x;
+        int a = 0, b = 0;
+        if (sl < n) { a = (seg_start[sl + 1] - seg_start[sl] + kW1Chunk - 1) / kW1Chunk; b = a > 1 ? a : 0; }
+        int ia = a, ib = b;                      // inclusive warp scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb2 = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ta; ib += tb2; }
+        }
+        if (lane == 31) { wsum_a[warp] = ia; wsum_b[warp] = ib; }
+        __syncthreads();
+        if (warp == 0) {
+            int va = wsum_a[lane], vb = wsum_b[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ta = __shfl_up_sync(0xffffffffu, va, o), tb2 = __shfl_up_sync(0xffffffffu, vb, o);
+                if (lane >= o) { va += ta; vb += tb2; }
+            }
+            wsum_a[lane] = va; wsum_b[lane] = vb;
+        }
+        __syncthreads();
+        const int offa = carry_a + (warp ? wsum_a[warp - 1] : 0), offb = carry_b + (warp ? wsum_b[warp - 1] : 0);
+        if (sl < n) { chunk_base[sl] = offa + ia - a; part_base[sl] = offb + ib - b; }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry_a += wsum_a[31]; carry_b += wsum_b[31]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { chunk_base[n] = carry_a; part_base[n] = carry_b; *n_work = carry_a; }
+}
+
+__global__ void w1_expand_kernel(const int32_t* __restrict__ n_unique, const int32_t* __restrict__ chunk_base,
+                                 int32_t* __restrict__ work_slot, int max_slots) {
+    const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sl >= max_slots || sl >= *n_unique) return;
+    for (int w = chunk_base[sl]; w < chunk_base[sl + 1]; ++w) work_slot[w] = sl;
+}
 template <int NCHUNK>
-__global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_unique,
+__global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_work,
+                                                      const int32_t* __restrict__ work_slot, const int32_t* __restrict__ chunk_base,
+                                                      const int32_t* __restrict__ part_base,
                                                       const int32_t* __restrict__ sorted_eid, const int32_t* __restrict__ ent_user,
                                                       const float* __restrict__ ent_val, const float* __restrict__ dpre, int ld4,
-                                                      float* __restrict__ gs, float* __restrict__ rownorm2) {
+                                                      int block_rows, int64_t block_stride4, float* __restrict__ gs,
+                                                      float* __restrict__ partial, float* __restrict__ rownorm2) {
+    // dpre row of batch position u: blocks of `block_rows` rows, `block_stride4` float4 apart (data-parallel training reads
+    // the all-gathered per-rank buffers in place); a plain [rows, ld] matrix has block_rows = INT_MAX.
     extern __shared__ float4 red[];  // [4][ld4]
-    const int slot = blockIdx.x;
-    if (slot >= *n_unique) return;
+    const int w = blockIdx.x;
+    if (w >= *n_work) return;
+    const int slot = work_slot[w];
+    const int cb = chunk_base[slot], nchunks = chunk_base[slot + 1] - cb, chunk = w - cb;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = seg_start[slot], e = seg_start[slot + 1];
+    const int s = seg_start[slot] + chunk * kW1Chunk, e = min(seg_start[slot + 1], s + kW1Chunk);
+    float* out_row = nchunks == 1 ? gs + (size_t)slot * ld4 * 4 : partial + (size_t)(part_base[slot] + chunk) * ld4 * 4;
     const float4* dp = reinterpret_cast<const float4*>(dpre);
     float4 a[NCHUNK];
 #pragma unroll
@@ -381,11 +440,13 @@ __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict_
         for (; t + 2 <= cnt; t += 2) {
             const int u0 = __shfl_sync(0xffffffffu, my_user, t), u1 = __shfl_sync(0xffffffffu, my_user, t + 1);
             const float v0 = __shfl_sync(0xffffffffu, my_val, t), v1 = __shfl_sync(0xffffffffu, my_val, t + 1);
+            const size_t o0 = (size_t)(u0 / block_rows) * block_stride4 + (size_t)(u0 % block_rows) * ld4;
+            const size_t o1 = (size_t)(u1 / block_rows) * block_stride4 + (size_t)(u1 % block_rows) * ld4;
             float4 g0[NCHUNK], g1[NCHUNK];
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
                 const int col4 = lane + 32 * c;
-                if (col4 < ld4) { g0[c] = __ldg(dp + (size_t)u0 * ld4 + col4); g1[c] = __ldg(dp + (size_t)u1 * ld4 + col4); }
+                if (col4 < ld4) { g0[c] = __ldg(dp + o0 + col4); g1[c] = __ldg(dp + o1 + col4); }
                 else { g0[c] = make_float4(0.f, 0.f, 0.f, 0.f); g1[c] = g0[c]; }
             }
 #pragma unroll
@@ -399,11 +460,12 @@ __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict_
         if (t < cnt) {
             const int u0 = __shfl_sync(0xffffffffu, my_user, t);
             const float v0 = __shfl_sync(0xffffffffu, my_val, t);
+            const size_t o0 = (size_t)(u0 / block_rows) * block_stride4 + (size_t)(u0 % block_rows) * ld4;
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
                 const int col4 = lane + 32 * c;
                 if (col4 < ld4) {
-                    const float4 g = __ldg(dp + (size_t)u0 * ld4 + col4);
+                    const float4 g = __ldg(dp + o0 + col4);
                     a[c].x = fmaf(v0, g.x, a[c].x); a[c].y = fmaf(v0, g.y, a[c].y);
                     a[c].z = fmaf(v0, g.z, a[c].z); a[c].w = fmaf(v0, g.w, a[c].w);
                 }
@@ -422,12 +484,39 @@ __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict_
         float4 o;
         o.x = (a0.x + b.x) + (c.x + d.x); o.y = (a0.y + b.y) + (c.y + d.y);
         o.z = (a0.z + b.z) + (c.z + d.z); o.w = (a0.w + b.w) + (c.w + d.w);
-        reinterpret_cast<float4*>(gs)[(size_t)slot * ld4 + col4] = o;
+        reinterpret_cast<float4*>(out_row)[col4] = o;
         n2 += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
     }
+    if (nchunks != 1) return;      // the norm of a multi-chunk row is taken after the combine
     __shared__ float wsum[4];
     n2 = warp_sum(n2);
     if (lane == 0) wsum[warp] = n2;
+    __syncthreads();
+    if (threadIdx.x == 0) rownorm2[slot] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+}
+
+// Items with several chunks: gs[slot] = partial rows added in chunk order; row norm.  One CTA per slot, early exit otherwise.
+__global__ void __launch_bounds__(128) w1_combine_kernel(const int32_t* __restrict__ n_unique, const int32_t* __restrict__ chunk_base,
+                                                         const int32_t* __restrict__ part_base, const float* __restrict__ partial,
+                                                         int ld4, float* __restrict__ gs, float* __restrict__ rownorm2) {
+    const int slot = blockIdx.x;
+    if (slot >= *n_unique) return;
+    const int nchunks = chunk_base[slot + 1] - chunk_base[slot];
+    if (nchunks <= 1) return;
+    const float4* pr = reinterpret_cast<const float4*>(partial) + (size_t)part_base[slot] * ld4;
+    float n2 = 0.f;
+    for (int col4 = threadIdx.x; col4 < ld4; col4 += 128) {
+        float4 a = pr[col4];
+        for (int c = 1; c < nchunks; ++c) {
+            const float4 b = pr[(size_t)c * ld4 + col4];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        reinterpret_cast<float4*>(gs)[(size_t)slot * ld4 + col4] = a;
+        n2 += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    __shared__ float wsum[4];
+    n2 = warp_sum(n2);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n2;
     __syncthreads();
     if (threadIdx.x == 0) rownorm2[slot] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
 }
@@ -534,22 +623,47 @@ int hvae_colsum(const float* X, int ld, int R, int C, float* out, float* workspa
     if (C == 0) return 0;
     const int chunks = max(1, min(64, ceil_div(R, 16)));
     const int rpc = ceil_div(max(R, 1), chunks);
+    if (chunks == 1) {   // few rows (e.g. the per-rank partial gradients of data-parallel training): one pass
+        colsum_chunk_kernel<<<dim3(ceil_div(C, 128), 1), 128, 0, (cudaStream_t)stream>>>(X, ld, R, C, R, out, C);
+        HVAE_LAUNCH_CHECK("colsum");
+        return 0;
+    }
     colsum_chunk_kernel<<<dim3(ceil_div(C, 128), chunks), 128, 0, (cudaStream_t)stream>>>(X, ld, R, C, rpc, workspace, C);
     colsum_chunk_kernel<<<dim3(ceil_div(C, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace, C, chunks, C, chunks, out, C);
     HVAE_LAUNCH_CHECK("colsum");
     return 0;
 }
 
+// Work plan of hvae_w1_grad for the transposed batch (depends on the batch only).  chunk_base, part_base: int32 [max_slots+1];
+// work_slot: int32 [hvae_w1_max_work(max_slots)]; n_work: int32 [1].
+size_t hvae_w1_max_work(int max_slots) { return (size_t)max_slots + (size_t)max_slots / kW1Chunk + 1; }
+size_t hvae_w1_max_partial_rows(int max_slots) { return 2 * ((size_t)max_slots / kW1Chunk + 1); }
+
+int hvae_w1_plan(const int32_t* seg_start, const int32_t* n_unique, int max_slots, int32_t* chunk_base, int32_t* part_base,
+                 int32_t* work_slot, int32_t* n_work, void* stream) {
+    if (max_slots == 0) return 0;
+    w1_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(seg_start, n_unique, chunk_base, part_base, n_work);
+    w1_expand_kernel<<<ceil_div(max_slots, 256), 256, 0, (cudaStream_t)stream>>>(n_unique, chunk_base, work_slot, max_slots);
+    HVAE_LAUNCH_CHECK("w1_plan");
+    return 0;
+}
+
 int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_t* sorted_eid, const int32_t* ent_user,
-                 const float* ent_val, int max_slots, const float* dpre, int ld, float* gs, float* rownorm2, void* stream) {
-    HVAE_REQUIRE(ld % 4 == 0, "w1_grad: ld=%d must be a multiple of 4", ld);
+                 const float* ent_val, int max_slots, const int32_t* chunk_base, const int32_t* part_base, const int32_t* work_slot,
+                 const int32_t* n_work, const float* dpre, int ld, int block_rows, int64_t block_stride, float* gs, float* partial,
+                 float* rownorm2, void* stream) {
+    HVAE_REQUIRE(ld % 4 == 0 && block_stride % 4 == 0, "w1_grad: ld=%d and the block stride must be multiples of 4", ld);
+    if (block_rows <= 0) { block_rows = 0x7fffffff; block_stride = 0; }
     if (max_slots == 0) return 0;
     const size_t smem = (size_t)4 * ld * sizeof(float);
     HVAE_REQUIRE(smem <= 48 * 1024, "w1_grad: hidden width %d too large", ld);
     const int h = ld;
     const int nch = ceil_div(ld / 4, 32);
-    DISPATCH_NCHUNK(nch, (w1_grad_kernel<NC><<<max_slots, 128, smem, (cudaStream_t)stream>>>(seg_start, n_unique, sorted_eid, ent_user,
-                                                                                             ent_val, dpre, ld / 4, gs, rownorm2)));
+    const int max_work = (int)hvae_w1_max_work(max_slots);
+    DISPATCH_NCHUNK(nch, (w1_grad_kernel<NC><<<max_work, 128, smem, (cudaStream_t)stream>>>(
+                             seg_start, n_work, work_slot, chunk_base, part_base, sorted_eid, ent_user, ent_val, dpre, ld / 4, block_rows,
+                             block_stride / 4, gs, partial, rownorm2)));
+    w1_combine_kernel<<<max_slots, 128, 0, (cudaStream_t)stream>>>(n_unique, chunk_base, part_base, partial, ld / 4, gs, rownorm2);
     HVAE_LAUNCH_CHECK("w1_grad");
     return 0;
 }

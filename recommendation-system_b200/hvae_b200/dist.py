@@ -4,10 +4,12 @@ The reference is single-process; these are the three ways its hot path shards on
 
 * training, data parallel over users (`DataParallel`): every rank holds the full model and the full
   interaction CSR (38 MB at 1M users).  A global batch is split evenly; each rank runs forward/backward on
-  its users with every mean taken over the GLOBAL batch (src/ml/model.py:281,287), then
-    - all-reduce(sum) of the small dense gradients (LayerNorm, biases, fc_mu/fc_logvar, projection; ~2 MB),
-    - all-gather of d(pre-activation of layer 1) [B_local, h] and of the batch's user ids; every rank then
-      reduces the layer-1 weight gradient of the WHOLE batch locally (deterministic segment sums).  The dense
+  its users with every mean taken over the GLOBAL batch (src/ml/model.py:281,287).  Two collectives per step:
+    - at the start, on a side stream: all-gather of the batch's user ids (2 KB), then the item-major transposition
+      of the GLOBAL batch -- overlapped with the forward pass;
+    - after backward: ONE all-gather of [small dense gradients (~2 MB) | d(pre-activation of layer 1) [B_local, h]]
+      per rank.  The dense gradients are summed over ranks by our own kernel in a fixed order; every rank reduces
+      the layer-1 weight gradient of the WHOLE batch locally, reading the gathered blocks in place.  The dense
       d(W1) [N, h] (480 MB at N=200k) never crosses NVLink.
   Gradient norm, clip coefficient and the fused Adam step are then identical on every rank.
 * evaluation, item-sharded (`ItemShard` + `sharded_topk`): rank g scores items [lo_g, hi_g) only, keeps a
@@ -134,15 +136,42 @@ class DataParallel:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         acc[:3] = t
 
-    # -- Engine hook (engine.Engine.train_step) -----------------------------------------------------------------
-    def exchange(self, eng, batch, dpre0):
+    # -- Engine hooks (engine.Engine.train_step) ----------------------------------------------------------------
+    # Every buffer is a persistent workspace tensor, so both collectives are captured into the step's CUDA graph.
+    def gather_batch(self, eng, batch):
+        """User ids of the global batch (tiny all-gather).  Needs nothing from the forward pass: the engine issues it on a
+        side stream at the start of the step, followed by the item-major transposition of the global batch."""
         from .engine import Batch
-        b_global = eng.b_global
-        self.reduce_dense(eng.gd)
         rows = batch.rows
         if rows is None:
             raise RuntimeError("data-parallel steps need explicit user ids (batch.rows)")
-        rows_all = self.gather_rows(rows, b_global)
-        dpre_all = self.gather_dpre(dpre0[:batch.B], b_global)
+        bm, B = self.b_max(eng.b_global), batch.B
+        send_rows = eng.ws.get("dp_rows_send", (bm,), torch.int32)
+        if B < bm:
+            send_rows.fill_(-1)
+        send_rows[:B].copy_(rows)
+        rows_all = eng.ws.get("dp_rows_all", (self.world * bm,), torch.int32)
+        dist.all_gather_into_tensor(rows_all, send_rows, group=self.group)
         cap = batch.nnz_cap_global if getattr(batch, "nnz_cap_global", None) else batch.nnz_cap * self.world
-        return Batch(batch.csr, rows_all, rows_all.shape[0], cap), dpre_all
+        return Batch(batch.csr, rows_all, rows_all.shape[0], cap)
+
+    def exchange_grads(self, eng, batch, dpre0):
+        """ONE all-gather per step: every rank sends [its dense gradients | its dH1 rows]; the dense gradients are then
+        summed over ranks in a fixed order by our column-sum kernel (identical bits on every rank) and the layer-1
+        weight-gradient kernel reads the gathered dH1 blocks in place.  -> (pointer to rank 0's dH1 block, rows per block,
+        block stride in floats)."""
+        from ._cabi import p
+        n_dense = eng.gd.numel()
+        bm, B, ld = self.b_max(eng.b_global), batch.B, dpre0.shape[1]
+        stride = n_dense + bm * ld
+        ws = eng.ws
+        send = ws.get("dp_send", (stride,))
+        send[:n_dense].copy_(eng.gd)
+        send[n_dense:n_dense + B * ld].copy_(dpre0[:B].reshape(-1))
+        if B < bm:
+            send[n_dense + B * ld:].zero_()
+        recv = ws.get("dp_recv", (self.world * stride,))
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        cs = ws.get("dp_colsum_ws", (n_dense + 64,))
+        eng.lib.colsum(p(recv), stride, self.world, n_dense, p(eng.gd), p(cs), eng.stream)
+        return recv.data_ptr() + 4 * n_dense, bm, stride

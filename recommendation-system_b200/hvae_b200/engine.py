@@ -530,23 +530,33 @@ class Engine:
                             p(arr["keys_sorted"]), p(arr["eid"]), p(arr["eid_sorted"]), p(arr["head"]), p(arr["slot"]),
                             p(arr["ent_user"]), p(ent_val), p(seg_start), p(arr["uniq_item"]), p(self.slot_of_item), p(n_unique),
                             p(overflow), p(temp), tb, st)
+        chunk_base = ws.get("w1_chunk_base", (cap + 1,), i32)
+        part_base = ws.get("w1_part_base", (cap + 1,), i32)
+        work_slot = ws.get("w1_work_slot", (int(lib.w1_max_work(cap)),), i32)
+        n_work = ws.get("w1_n_work", (1,), i32, zero=True)
+        lib.w1_plan(p(seg_start), p(n_unique), cap, p(chunk_base), p(part_base), p(work_slot), p(n_work), st)
         return dict(cap=cap, seg_start=seg_start, n_unique=n_unique, eid_sorted=arr["eid_sorted"], ent_user=arr["ent_user"],
-                    ent_val=ent_val, uniq=arr["uniq_item"])
+                    ent_val=ent_val, uniq=arr["uniq_item"], chunk_base=chunk_base, part_base=part_base, work_slot=work_slot,
+                    n_work=n_work)
 
-    def w1_grad(self, tb, dpre0):
-        """d(W1^T) rows of the touched items (deterministic segment sums) and their squared norms."""
+    def w1_grad(self, tb, dpre_ptr, block_rows=0, block_stride=0):
+        """d(W1^T) rows of the touched items (deterministic segment sums) and their squared norms.  dpre_ptr: device
+        pointer of the batch's d(pre-activation) rows (optionally blocked: see hvae_w1_grad)."""
         ws, lib = self.ws, self.lib
         ld1 = r4(self.lay.hidden[0])
-        gs = ws.get("gs", (tb["cap"], ld1))
+        n_rows = min(tb["cap"], self.lay.N)            # at most one gradient row per item
+        gs = ws.get("gs", (n_rows, ld1))
         rn2 = ws.get("rownorm2", (tb["cap"],))
+        part = ws.get("w1_partial", (int(lib.w1_max_partial_rows(tb["cap"])), ld1))
         lib.w1_grad(p(tb["seg_start"]), p(tb["n_unique"]), p(tb["eid_sorted"]), p(tb["ent_user"]), p(tb["ent_val"]), tb["cap"],
-                    p(dpre0), ld1, p(gs), p(rn2), self.stream)
+                    p(tb["chunk_base"]), p(tb["part_base"]), p(tb["work_slot"]), p(tb["n_work"]), dpre_ptr, ld1, block_rows,
+                    block_stride, p(gs), p(part), p(rn2), self.stream)
         return gs, rn2
 
     def sparse_w1_grad(self, batch: Batch, dpre0, B=None):
         """Transpose the batch by item and reduce d(W1^T) rows (deterministic)."""
         tb = self.transpose_batch(batch)
-        gs, rn2 = self.w1_grad(tb, dpre0)
+        gs, rn2 = self.w1_grad(tb, p(dpre0))
         return gs, rn2, tb["n_unique"], tb["uniq"]
 
     def train_step(self, batch: Batch, noise, lr=1e-3, weight_decay=0.0, beta_min=0.0, beta_max=0.2, anneal_steps=0,
@@ -557,21 +567,20 @@ class Engine:
         b_global = batch.B if b_global is None else b_global
         self.b_global = b_global
         self.begin(b_global, lr, beta_min, beta_max, anneal_steps, advance=True, noise_stride=noise_stride)
-        tb = None
-        if self.dist is None:            # the item-major view of the batch does not depend on the forward pass
-            with self.side(2), self.span("transpose"):
-                tb = self.transpose_batch(batch)
+        # the item-major view of the (global) batch does not depend on the forward pass: side stream
+        with self.side(2), self.span("transpose"):
+            wbatch = batch if self.dist is None else self.dist.gather_batch(self, batch)
+            tb = self.transpose_batch(wbatch)
         ml, u, O, oscale = self.forward_loss(batch, noise, want_grad=True)
         with self.span("bwd_dense"):
             self.backward(batch, noise, ml, O, oscale)
-        wbatch, dpre0 = batch, self.dpre0
+        self.join()
+        dpre_ptr, block_rows, block_stride = p(self.dpre0), 0, 0
         if self.dist is not None:
             with self.span("exchange"):
-                wbatch, dpre0 = self.dist.exchange(self, batch, dpre0)
-            tb = self.transpose_batch(wbatch)
-        self.join()
+                dpre_ptr, block_rows, block_stride = self.dist.exchange_grads(self, batch, self.dpre0)
         with self.span("w1grad"):
-            gs, rn2 = self.w1_grad(tb, dpre0)
+            gs, rn2 = self.w1_grad(tb, dpre_ptr, block_rows, block_stride)
         n_unique, uniq = tb["n_unique"], tb["uniq"]
         gn_ws = self.ws.get("gn_ws", (256,))
         lib.grad_norm_clip(p(self.gd), lay.n_dense, p(rn2), p(n_unique), self.MAX_NORM, p(self.state), p(gn_ws), st)

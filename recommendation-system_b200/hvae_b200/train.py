@@ -165,6 +165,7 @@ class VAETrainer:
         self._loaders = {}
         self._graphs = {}
         self._anneal_dev = 0        # device copy of AnnealedVAE.current_step (hvae_step_state.anneal_step)
+        self.graph_collectives = True   # data parallel: capture the NCCL exchange into the step graph as well
         logger.info("Trainer on %s, %s params", device, f"{self.model.num_parameters():,}")
 
     # -- multi-GPU ---------------------------------------------------------------------------------------------
@@ -259,13 +260,16 @@ class VAETrainer:
         cap = max(1024, -(-int(batch.nnz_cap * 1.05) // 1024) * 1024)        # bucketed so that re-captures are rare
         key = (kind, batch.B, b_global, self.lr, self.weight_decay)
         ent = self._graphs.get(key)
-        if ent is not None and ent["cap"] >= batch.nnz_cap and ent["gen"] == eng.ws.generation:
+        capg_need = getattr(batch, "nnz_cap_global", None) or 0
+        if (ent is not None and ent["cap"] >= batch.nnz_cap and ent["cap_global"] >= capg_need
+                and ent["gen"] == eng.ws.generation):
             return ent
         dev, B = self.device, batch.B
-        ent = {"cap": cap, "graph": None, "launches": 0, "gen": eng.ws.generation}
+        capg = max(1024, -(-int(capg_need * 1.05) // 1024) * 1024) if capg_need else None
+        ent = {"cap": cap, "cap_global": capg or 0, "graph": None, "launches": 0, "gen": eng.ws.generation}
         if kind == "rows":      # batch = user ids into the resident CSR
             ent["rows"] = torch.zeros(B, dtype=torch.int32, device=dev)
-            ent["batch"] = Batch(batch.csr, ent["rows"], B, cap, b_global=batch.b_global, nnz_cap_global=batch.nnz_cap_global)
+            ent["batch"] = Batch(batch.csr, ent["rows"], B, cap, b_global=batch.b_global, nnz_cap_global=capg)
             ent["csr_id"] = id(batch.csr)
         else:                   # batch = its own CSR slice copied from the host every step
             ent["crow"] = torch.zeros(B + 1, dtype=torch.int64, device=dev)
@@ -323,8 +327,8 @@ class VAETrainer:
         m = self.model
         eng = m.engine
         self._sync_anneal_step()
-        graphable = (noise is None and self.use_cuda_graph and self.noise_mode == "philox" and eng.dist is None
-                     and eng.prof is None)
+        graphable = (noise is None and self.use_cuda_graph and self.noise_mode == "philox" and eng.prof is None
+                     and (eng.dist is None or (self.graph_collectives and batch.rows is not None)))
         if graphable:
             self._graphed_step(batch, b_global)
         else:
