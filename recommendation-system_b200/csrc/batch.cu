@@ -10,6 +10,7 @@ namespace hvae {
 
 __global__ void __launch_bounds__(1024) batch_offsets_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ rows, int B,
                                                               int32_t* __restrict__ boff) {
+    pdl_prologue();
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int carry;
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(1024) batch_offsets_kernel(const int64_t* __re
 }
 
 __global__ void fill_keys_kernel(int32_t* __restrict__ keys, int32_t* __restrict__ eid, int cap, int sentinel) {
+    pdl_prologue();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < cap) { keys[e] = sentinel; eid[e] = e; }
 }
@@ -37,6 +39,7 @@ __global__ void expand_kernel(const int64_t* __restrict__ indptr, const int32_t*
                               const int32_t* __restrict__ rows, int B, const int32_t* __restrict__ boff, int cap,
                               int32_t* __restrict__ keys, int32_t* __restrict__ ent_user, float* __restrict__ ent_val,
                               int32_t* __restrict__ overflow) {
+    pdl_prologue();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     const int u = rows ? rows[b] : b;
@@ -52,6 +55,7 @@ __global__ void expand_kernel(const int64_t* __restrict__ indptr, const int32_t*
 }
 
 __global__ void seg_heads_kernel(const int32_t* __restrict__ keys, int cap, int sentinel, int32_t* __restrict__ head) {
+    pdl_prologue();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= cap) return;
     const int k = keys[e];
@@ -61,6 +65,7 @@ __global__ void seg_heads_kernel(const int32_t* __restrict__ keys, int cap, int 
 __global__ void seg_write_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ head, const int32_t* __restrict__ slot,
                                  int cap, int sentinel, int32_t* __restrict__ seg_start, int32_t* __restrict__ uniq_item,
                                  int32_t* __restrict__ slot_of_item, int32_t* __restrict__ n_unique) {
+    pdl_prologue();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= cap) return;
     const int k = keys[e];
@@ -76,6 +81,7 @@ __global__ void seg_write_kernel(const int32_t* __restrict__ keys, const int32_t
 
 __global__ void batch_release_kernel(const int32_t* __restrict__ uniq_item, const int32_t* __restrict__ n_unique, int cap,
                                      int32_t* __restrict__ slot_of_item) {
+    pdl_prologue();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < cap && s < *n_unique) slot_of_item[uniq_item[s]] = -1;
 }
@@ -101,7 +107,7 @@ size_t hvae_batch_temp_bytes(int cap, int n_items) {
 }
 
 int hvae_batch_offsets(const int64_t* indptr, const int32_t* rows, int B, int32_t* boff, void* stream) {
-    batch_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(indptr, rows, B, boff);
+    launch_pdl(batch_offsets_kernel, 1, 1024, 0, (cudaStream_t)stream, indptr, rows, B, boff);
     HVAE_LAUNCH_CHECK("batch_offsets");
     return 0;
 }
@@ -116,22 +122,22 @@ int hvae_batch_transpose(const int64_t* indptr, const int32_t* indices, const fl
     HVAE_REQUIRE(cap >= 1, "batch_transpose: cap must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
     const int tb = 256, gb = ceil_div(cap, tb);
-    fill_keys_kernel<<<gb, tb, 0, st>>>(keys, eid, cap, n_items);
+    launch_pdl(fill_keys_kernel, gb, tb, 0, st, keys, eid, cap, n_items);
     if (B > 0)
-        expand_kernel<<<ceil_div(B, 8), 256, 0, st>>>(indptr, indices, values, rows, B, boff, cap, keys, ent_user, ent_val, overflow);
+        launch_pdl(expand_kernel, ceil_div(B, 8), 256, 0, st, indptr, indices, values, rows, B, boff, cap, keys, ent_user, ent_val, overflow);
     size_t need = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys_sorted, eid, eid_sorted, cap, 0, key_bits(n_items), st);
     HVAE_REQUIRE(need <= temp_bytes, "batch_transpose: temp storage %zu < %zu", temp_bytes, need);
     HVAE_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_sorted, eid, eid_sorted, cap, 0, key_bits(n_items), st));
-    seg_heads_kernel<<<gb, tb, 0, st>>>(keys_sorted, cap, n_items, head);
+    launch_pdl(seg_heads_kernel, gb, tb, 0, st, keys_sorted, cap, n_items, head);
     HVAE_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, head, slot, cap, st));
-    seg_write_kernel<<<gb, tb, 0, st>>>(keys_sorted, head, slot, cap, n_items, seg_start, uniq_item, slot_of_item, n_unique);
+    launch_pdl(seg_write_kernel, gb, tb, 0, st, keys_sorted, head, slot, cap, n_items, seg_start, uniq_item, slot_of_item, n_unique);
     HVAE_LAUNCH_CHECK("batch_transpose");
     return 0;
 }
 
 int hvae_batch_release(const int32_t* uniq_item, const int32_t* n_unique, int cap, int32_t* slot_of_item, void* stream) {
-    batch_release_kernel<<<ceil_div(cap, 256), 256, 0, (cudaStream_t)stream>>>(uniq_item, n_unique, cap, slot_of_item);
+    launch_pdl(batch_release_kernel, ceil_div(cap, 256), 256, 0, (cudaStream_t)stream, uniq_item, n_unique, cap, slot_of_item);
     HVAE_LAUNCH_CHECK("batch_release");
     return 0;
 }

@@ -27,6 +27,33 @@ namespace hvae {
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute and starts with
+// pdl_prologue(): "my dependents may start launching" + "wait until the kernel(s) before me have completed and flushed".
+// Inside a captured step this overlaps the launch latency / prologue of kernel N+1 with the execution of kernel N (the
+// tensor-core kernels do their barrier init, TMEM allocation and descriptor prefetch before the wait).  Without the
+// attribute both instructions are no-ops.  HVAE_NO_PDL=1 disables the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+
+bool pdl_enabled();   // capi.cu
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

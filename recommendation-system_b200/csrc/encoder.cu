@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) gather_ln_fwd_kernel(
     const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
     const uint8_t* __restrict__ mask, float keep_scale, float* __restrict__ pre, float* __restrict__ mean_out,
     float* __restrict__ rstd_out, float* __restrict__ act) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= B) return;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(512) gather_ln_fwd_block_kernel(
     const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
     const uint8_t* __restrict__ mask, float keep_scale, float* __restrict__ pre, float* __restrict__ mean_out,
     float* __restrict__ rstd_out, float* __restrict__ act) {
+    pdl_prologue();
     __shared__ float stat[2];
     const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int u = rows ? rows[b] : b;
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(256) ln_act_fwd_kernel(const float* __restrict
                                                          const uint8_t* __restrict__ mask, float keep_scale,
                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                          float* __restrict__ act) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= B) return;
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(256) ln_act_bwd_kernel(const float* dact, cons
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const uint8_t* __restrict__ mask, float keep_scale, int B, int h,
                                                          int ld4, float* dpre, float* __restrict__ partial) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -333,6 +337,7 @@ __global__ void __launch_bounds__(256) ln_act_bwd_kernel(const float* dact, cons
 // out[chunk][c] = sum over rows r in [chunk*rpc, min(R,(chunk+1)*rpc)) of X[r][c]   (fixed order)
 __global__ void colsum_chunk_kernel(const float* __restrict__ X, int ld, int R, int C, int rpc, float* __restrict__ out,
                                     int out_ld) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int r0 = blockIdx.y * rpc, r1 = min(R, r0 + rpc);
@@ -366,6 +371,7 @@ constexpr int kW1Chunk = 64;
 __global__ void __launch_bounds__(1024) w1_plan_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_unique,
                                                         int32_t* __restrict__ chunk_base, int32_t* __restrict__ part_base,
                                                         int32_t* __restrict__ n_work) {
+    pdl_prologue();
     __shared__ int wsum_a[32], wsum_b[32];
     __shared__ int carry_a, carry_b;
     const int n = *n_unique, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -404,6 +410,7 @@ __global__ void __launch_bounds__(1024) w1_plan_kernel(const int32_t* __restrict
 
 __global__ void w1_expand_kernel(const int32_t* __restrict__ n_unique, const int32_t* __restrict__ chunk_base,
                                  int32_t* __restrict__ work_slot, int max_slots) {
+    pdl_prologue();
     const int sl = blockIdx.x * blockDim.x + threadIdx.x;
     if (sl >= max_slots || sl >= *n_unique) return;
     for (int w = chunk_base[sl]; w < chunk_base[sl + 1]; ++w) work_slot[w] = sl;
@@ -416,6 +423,7 @@ __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict_
                                                       const float* __restrict__ ent_val, const float* __restrict__ dpre, int ld4,
                                                       int block_rows, int64_t block_stride4, float* __restrict__ gs,
                                                       float* __restrict__ partial, float* __restrict__ rownorm2) {
+    pdl_prologue();
     // dpre row of batch position u: blocks of `block_rows` rows, `block_stride4` float4 apart (data-parallel training reads
     // the all-gathered per-rank buffers in place); a plain [rows, ld] matrix has block_rows = INT_MAX.
     extern __shared__ float4 red[];  // [4][ld4]
@@ -499,6 +507,7 @@ __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict_
 __global__ void __launch_bounds__(128) w1_combine_kernel(const int32_t* __restrict__ n_unique, const int32_t* __restrict__ chunk_base,
                                                          const int32_t* __restrict__ part_base, const float* __restrict__ partial,
                                                          int ld4, float* __restrict__ gs, float* __restrict__ rownorm2) {
+    pdl_prologue();
     const int slot = blockIdx.x;
     if (slot >= *n_unique) return;
     const int nchunks = chunk_base[slot + 1] - chunk_base[slot];
@@ -525,6 +534,7 @@ __global__ void __launch_bounds__(128) w1_combine_kernel(const int32_t* __restri
 __global__ void w1_grad_dense_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                      const float* __restrict__ values, const int32_t* __restrict__ rows, int B,
                                      const float* __restrict__ dpre, int ld, int h, float* __restrict__ dW1T) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= B) return;
@@ -563,7 +573,7 @@ int hvae_gather_ln_fwd(const int64_t* indptr, const int32_t* indices, const floa
     HVAE_REQUIRE(ld % 4 == 0 && ld >= h, "gather_ln_fwd: ld=%d must be a multiple of 4 and >= h=%d", ld, h);
     if (B == 0) return 0;
     if (B < 2048 && ld / 4 <= 512) {   // small batch: one CTA per user (more loads in flight)
-        gather_ln_fwd_block_kernel<<<B, round_up(ld / 4, 32), (size_t)ld * sizeof(float), (cudaStream_t)stream>>>(
+        launch_pdl(gather_ln_fwd_block_kernel, B, round_up(ld / 4, 32), (size_t)ld * sizeof(float), (cudaStream_t)stream, 
             indptr, indices, values, rows, B, reinterpret_cast<const float4*>(W1T), ld / 4, h, bias, gamma, beta, mask, keep_scale, pre,
             mean, rstd, act);
         HVAE_LAUNCH_CHECK("gather_ln_fwd(block)");
@@ -571,7 +581,7 @@ int hvae_gather_ln_fwd(const int64_t* indptr, const int32_t* indices, const floa
     }
     const int nch = ceil_div(ld / 4, 32);
     const int blocks = ceil_div(B, 8);
-    DISPATCH_NCHUNK(nch, (gather_ln_fwd_kernel<NC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    DISPATCH_NCHUNK(nch, (launch_pdl(gather_ln_fwd_kernel<NC>, blocks, 256, 0, (cudaStream_t)stream, 
                              indptr, indices, values, rows, B, reinterpret_cast<const float4*>(W1T), ld / 4, h, bias,
                              gamma, beta, mask, keep_scale, pre, mean, rstd, act)));
     HVAE_LAUNCH_CHECK("gather_ln_fwd");
@@ -583,7 +593,7 @@ int hvae_ln_act_fwd(const float* pre, int B, int h, int ld, const float* gamma, 
     HVAE_REQUIRE(ld % 4 == 0 && ld >= h, "ln_act_fwd: bad ld=%d h=%d", ld, h);
     if (B == 0) return 0;
     const int nch = ceil_div(ld / 4, 32);
-    DISPATCH_NCHUNK(nch, (ln_act_fwd_kernel<NC><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
+    DISPATCH_NCHUNK(nch, (launch_pdl(ln_act_fwd_kernel<NC>, ceil_div(B, 8), 256, 0, (cudaStream_t)stream, 
                              pre, B, h, ld / 4, gamma, beta, mask, keep_scale, mean, rstd, act)));
     HVAE_LAUNCH_CHECK("ln_act_fwd");
     return 0;
@@ -603,16 +613,16 @@ int hvae_ln_act_bwd(const float* dact, const float* pre, const float* mean, cons
     const int blocks = ln_bwd_blocks(B);
     const size_t smem = (size_t)2 * ld * sizeof(float);
     HVAE_REQUIRE(smem <= 48 * 1024, "ln_act_bwd: hidden width %d too large", ld);
-    DISPATCH_NCHUNK(nch, (ln_act_bwd_kernel<NC><<<blocks, 256, smem, (cudaStream_t)stream>>>(
+    DISPATCH_NCHUNK(nch, (launch_pdl(ln_act_bwd_kernel<NC>, blocks, 256, smem, (cudaStream_t)stream, 
                              dact, pre, mean, rstd, gamma, beta, mask, keep_scale, B, h, ld / 4, dpre, workspace)));
     HVAE_LAUNCH_CHECK("ln_act_bwd");
     // one partial row per block, [2*ld] wide: first ld = d(gamma), next ld = d(beta)
     const int R = blocks;
     if (dbeta == dgamma + ld) {   // adjacent slots of the gradient arena: one launch over both (pad columns of the partials are zero)
-        colsum_chunk_kernel<<<dim3(ceil_div(2 * ld, 64), 1), 64, 0, (cudaStream_t)stream>>>(workspace, 2 * ld, R, 2 * ld, R, dgamma, 2 * ld);
+        launch_pdl(colsum_chunk_kernel, dim3(ceil_div(2 * ld, 64), 1), 64, 0, (cudaStream_t)stream, workspace, 2 * ld, R, 2 * ld, R, dgamma, 2 * ld);
     } else {
-        colsum_chunk_kernel<<<dim3(ceil_div(h, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace, 2 * ld, R, h, R, dgamma, h);
-        colsum_chunk_kernel<<<dim3(ceil_div(h, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace + ld, 2 * ld, R, h, R, dbeta, h);
+        launch_pdl(colsum_chunk_kernel, dim3(ceil_div(h, 128), 1), 128, 0, (cudaStream_t)stream, workspace, 2 * ld, R, h, R, dgamma, h);
+        launch_pdl(colsum_chunk_kernel, dim3(ceil_div(h, 128), 1), 128, 0, (cudaStream_t)stream, workspace + ld, 2 * ld, R, h, R, dbeta, h);
     }
     HVAE_LAUNCH_CHECK("ln_act_bwd colsum");
     return 0;
@@ -624,12 +634,12 @@ int hvae_colsum(const float* X, int ld, int R, int C, float* out, float* workspa
     const int chunks = max(1, min(64, ceil_div(R, 16)));
     const int rpc = ceil_div(max(R, 1), chunks);
     if (chunks == 1) {   // few rows (e.g. the per-rank partial gradients of data-parallel training): one pass
-        colsum_chunk_kernel<<<dim3(ceil_div(C, 128), 1), 128, 0, (cudaStream_t)stream>>>(X, ld, R, C, R, out, C);
+        launch_pdl(colsum_chunk_kernel, dim3(ceil_div(C, 128), 1), 128, 0, (cudaStream_t)stream, X, ld, R, C, R, out, C);
         HVAE_LAUNCH_CHECK("colsum");
         return 0;
     }
-    colsum_chunk_kernel<<<dim3(ceil_div(C, 128), chunks), 128, 0, (cudaStream_t)stream>>>(X, ld, R, C, rpc, workspace, C);
-    colsum_chunk_kernel<<<dim3(ceil_div(C, 128), 1), 128, 0, (cudaStream_t)stream>>>(workspace, C, chunks, C, chunks, out, C);
+    launch_pdl(colsum_chunk_kernel, dim3(ceil_div(C, 128), chunks), 128, 0, (cudaStream_t)stream, X, ld, R, C, rpc, workspace, C);
+    launch_pdl(colsum_chunk_kernel, dim3(ceil_div(C, 128), 1), 128, 0, (cudaStream_t)stream, workspace, C, chunks, C, chunks, out, C);
     HVAE_LAUNCH_CHECK("colsum");
     return 0;
 }
@@ -642,8 +652,8 @@ size_t hvae_w1_max_partial_rows(int max_slots) { return 2 * ((size_t)max_slots /
 int hvae_w1_plan(const int32_t* seg_start, const int32_t* n_unique, int max_slots, int32_t* chunk_base, int32_t* part_base,
                  int32_t* work_slot, int32_t* n_work, void* stream) {
     if (max_slots == 0) return 0;
-    w1_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(seg_start, n_unique, chunk_base, part_base, n_work);
-    w1_expand_kernel<<<ceil_div(max_slots, 256), 256, 0, (cudaStream_t)stream>>>(n_unique, chunk_base, work_slot, max_slots);
+    launch_pdl(w1_plan_kernel, 1, 1024, 0, (cudaStream_t)stream, seg_start, n_unique, chunk_base, part_base, n_work);
+    launch_pdl(w1_expand_kernel, ceil_div(max_slots, 256), 256, 0, (cudaStream_t)stream, n_unique, chunk_base, work_slot, max_slots);
     HVAE_LAUNCH_CHECK("w1_plan");
     return 0;
 }
@@ -660,10 +670,10 @@ int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_
     const int h = ld;
     const int nch = ceil_div(ld / 4, 32);
     const int max_work = (int)hvae_w1_max_work(max_slots);
-    DISPATCH_NCHUNK(nch, (w1_grad_kernel<NC><<<max_work, 128, smem, (cudaStream_t)stream>>>(
+    DISPATCH_NCHUNK(nch, (launch_pdl(w1_grad_kernel<NC>, max_work, 128, smem, (cudaStream_t)stream, 
                              seg_start, n_work, work_slot, chunk_base, part_base, sorted_eid, ent_user, ent_val, dpre, ld / 4, block_rows,
                              block_stride / 4, gs, partial, rownorm2)));
-    w1_combine_kernel<<<max_slots, 128, 0, (cudaStream_t)stream>>>(n_unique, chunk_base, part_base, partial, ld / 4, gs, rownorm2);
+    launch_pdl(w1_combine_kernel, max_slots, 128, 0, (cudaStream_t)stream, n_unique, chunk_base, part_base, partial, ld / 4, gs, rownorm2);
     HVAE_LAUNCH_CHECK("w1_grad");
     return 0;
 }
@@ -671,7 +681,7 @@ int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_
 int hvae_w1_grad_dense(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
                        const float* dpre, int ld, int h, float* dW1T, void* stream) {
     if (B == 0) return 0;
-    w1_grad_dense_kernel<<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, dpre, ld, h, dW1T);
+    launch_pdl(w1_grad_dense_kernel, ceil_div(B, 8), 256, 0, (cudaStream_t)stream, indptr, indices, values, rows, B, dpre, ld, h, dW1T);
     HVAE_LAUNCH_CHECK("w1_grad_dense");
     return 0;
 }

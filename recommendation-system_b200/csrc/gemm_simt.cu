@@ -15,6 +15,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_kernel(int M, 
                                                                          int64_t a_cs, const float* __restrict__ Bm, int64_t b_rs,
                                                                          int64_t b_cs, float* __restrict__ C, int64_t ldc,
                                                                          const float* __restrict__ bias, float alpha) {
+    pdl_prologue();
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int LA = BM * GBK / NT, LB = BN * GBK / NT;     // elements each thread stages per k-block
     static_assert(LA >= 1 && LB >= 1 && TM % 4 == 0 && TN == 4, "tile configuration");
@@ -110,11 +111,11 @@ extern "C" int hvae_gemm_f32(int M, int N, int K, const float* A, int64_t a_rs, 
     if (big_ctas >= 2 * kNumSMs) {
         dim3 grid(ceil_div(N, 64), ceil_div(M, 128));
         HVAE_REQUIRE(grid.y <= 65535, "gemm_f32: M=%d too large for one launch", M);
-        gemm_f32_kernel<128, 64, 8, 4, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha);
+        launch_pdl(gemm_f32_kernel<128, 64, 8, 4, 16>, grid, 256, 0, (cudaStream_t)stream, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha);
     } else {
         dim3 grid(ceil_div(N, 64), ceil_div(M, 32));
         HVAE_REQUIRE(grid.y <= 65535, "gemm_f32: M=%d too large for one launch", M);
-        gemm_f32_kernel<32, 64, 4, 4, 64><<<grid, 128, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha);
+        launch_pdl(gemm_f32_kernel<32, 64, 4, 4, 64>, grid, 128, 0, (cudaStream_t)stream, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha);
     }
     HVAE_LAUNCH_CHECK("gemm_f32");
     return 0;

@@ -89,6 +89,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 
 __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB, TGemmParams P) {
+    pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int TG_STAGES = P.n_stages, TG_STAGE = P.stage_bytes;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
 
     if (warp == 0) {
         if (lane == 0) {
@@ -285,7 +287,7 @@ int hvae_gemm_tf32(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_
         attr_set = true;
     }
     dim3 grid(ceil_div(N, TG_BN), ceil_div(M, TG_BM));
-    gemm_tf32_kernel<<<grid, TG_THREADS, kTGemmSmem, (cudaStream_t)stream>>>(tmA, tmB, P);
+    launch_pdl(gemm_tf32_kernel, grid, TG_THREADS, kTGemmSmem, (cudaStream_t)stream, tmA, tmB, P);
     HVAE_LAUNCH_CHECK("gemm_tf32");
     return 0;
 }

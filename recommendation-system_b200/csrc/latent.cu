@@ -9,6 +9,7 @@ namespace hvae {
 // kl_row[b] = -0.5 * sum_j (1 + lv - mu^2 - exp(lv)).
 __global__ void reparam_kl_kernel(const float* __restrict__ ml, int ldml, const float* __restrict__ eps, int B, int L,
                                   float* __restrict__ z, int ldz, float* __restrict__ kl_row) {
+    pdl_prologue();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= B) return;
     const float* mu = ml + (size_t)row * ldml;
@@ -32,6 +33,7 @@ __global__ void reparam_kl_kernel(const float* __restrict__ ml, int ldml, const 
 __global__ void latent_bwd_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ ml, int ldml,
                                   const float* __restrict__ eps, int B, int L, const float* __restrict__ coef,
                                   float* __restrict__ dml) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * L) return;
     const int row = i / L, j = i - row * L;
@@ -47,6 +49,7 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dz, int lddz, const 
 // t = gelu(q) * mask * keep_scale  (mask may be null)
 __global__ void gelu_drop_fwd_kernel(const float* __restrict__ q, const uint8_t* __restrict__ mask, float keep_scale, int B,
                                      int d, int ld, float* __restrict__ t) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * ld) return;
     const int row = i / ld, j = i - row * ld;
@@ -61,6 +64,7 @@ __global__ void gelu_drop_fwd_kernel(const float* __restrict__ q, const uint8_t*
 // dq = dt * mask * keep_scale * gelu'(q)   (dt may alias dq)
 __global__ void gelu_drop_bwd_kernel(const float* dt, const float* __restrict__ q, const uint8_t* __restrict__ mask,
                                      float keep_scale, int B, int d, int ld, float* dq) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * ld) return;
     const int row = i / ld, j = i - row * ld;
@@ -80,6 +84,7 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __rest
                                                               int B, const float* __restrict__ inv_bg,
                                                               const float* __restrict__ beta, float* __restrict__ out,
                                                               float* __restrict__ acc) {
+    pdl_prologue();
     __shared__ double sr[32], sk[32];
     double r = 0.0, k = 0.0;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -110,7 +115,7 @@ extern "C" {
 
 int hvae_reparam_kl(const float* ml, int ldml, const float* eps, int B, int L, float* z, int ldz, float* kl_row, void* stream) {
     if (B == 0) return 0;
-    reparam_kl_kernel<<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(ml, ldml, eps, B, L, z, ldz, kl_row);
+    launch_pdl(reparam_kl_kernel, ceil_div(B, 8), 256, 0, (cudaStream_t)stream, ml, ldml, eps, B, L, z, ldz, kl_row);
     HVAE_LAUNCH_CHECK("reparam_kl");
     return 0;
 }
@@ -118,14 +123,14 @@ int hvae_reparam_kl(const float* ml, int ldml, const float* eps, int B, int L, f
 int hvae_latent_bwd(const float* dz, int lddz, const float* ml, int ldml, const float* eps, int B, int L, const float* coef,
                     float* dml, void* stream) {
     if (B == 0) return 0;
-    latent_bwd_kernel<<<ceil_div(B * L, 256), 256, 0, (cudaStream_t)stream>>>(dz, lddz, ml, ldml, eps, B, L, coef, dml);
+    launch_pdl(latent_bwd_kernel, ceil_div(B * L, 256), 256, 0, (cudaStream_t)stream, dz, lddz, ml, ldml, eps, B, L, coef, dml);
     HVAE_LAUNCH_CHECK("latent_bwd");
     return 0;
 }
 
 int hvae_gelu_drop_fwd(const float* q, const uint8_t* mask, float keep_scale, int B, int d, int ld, float* t, void* stream) {
     if (B == 0) return 0;
-    gelu_drop_fwd_kernel<<<ceil_div(B * ld, 256), 256, 0, (cudaStream_t)stream>>>(q, mask, keep_scale, B, d, ld, t);
+    launch_pdl(gelu_drop_fwd_kernel, ceil_div(B * ld, 256), 256, 0, (cudaStream_t)stream, q, mask, keep_scale, B, d, ld, t);
     HVAE_LAUNCH_CHECK("gelu_drop_fwd");
     return 0;
 }
@@ -133,14 +138,14 @@ int hvae_gelu_drop_fwd(const float* q, const uint8_t* mask, float keep_scale, in
 int hvae_gelu_drop_bwd(const float* dt, const float* q, const uint8_t* mask, float keep_scale, int B, int d, int ld, float* dq,
                        void* stream) {
     if (B == 0) return 0;
-    gelu_drop_bwd_kernel<<<ceil_div(B * ld, 256), 256, 0, (cudaStream_t)stream>>>(dt, q, mask, keep_scale, B, d, ld, dq);
+    launch_pdl(gelu_drop_bwd_kernel, ceil_div(B * ld, 256), 256, 0, (cudaStream_t)stream, dt, q, mask, keep_scale, B, d, ld, dq);
     HVAE_LAUNCH_CHECK("gelu_drop_bwd");
     return 0;
 }
 
 int hvae_loss_finalize(const float* lse, const float* dot, const float* xsum, const float* kl_row, int B, const float* inv_bg,
                        const float* beta, float* out, float* acc, void* stream) {
-    loss_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lse, dot, xsum, kl_row, B, inv_bg, beta, out, acc);
+    launch_pdl(loss_finalize_kernel, 1, 1024, 0, (cudaStream_t)stream, lse, dot, xsum, kl_row, B, inv_bg, beta, out, acc);
     HVAE_LAUNCH_CHECK("loss_finalize");
     return 0;
 }

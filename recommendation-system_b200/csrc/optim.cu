@@ -10,6 +10,7 @@ namespace hvae {
 // All step-dependent scalars live on the device so that a captured CUDA graph can be replayed unchanged.
 __global__ void step_begin_kernel(hvae_step_state* st, double lr, double b1, double b2, double beta_min, double beta_max,
                                   int anneal_steps, int b_global, int advance_adam, uint32_t noise_stride) {
+    pdl_prologue();
     if (advance_adam) {
         const int step = ++st->adam_step;
         const double bc1 = 1.0 - pow(b1, (double)step);
@@ -34,6 +35,7 @@ __global__ void step_begin_kernel(hvae_step_state* st, double lr, double b1, dou
 }
 
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partial) {
+    pdl_prologue();
     float s = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = fmaf(g[i], g[i], s);
     __shared__ float red[8];
@@ -52,6 +54,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 __global__ void __launch_bounds__(1024) gradnorm_final_kernel(const float* __restrict__ partial, int npartial,
                                                                const float* __restrict__ rownorm2, const int32_t* __restrict__ n_unique,
                                                                float max_norm, hvae_step_state* st) {
+    pdl_prologue();
     __shared__ double red[32];
     double s = 0.0;
     for (int i = threadIdx.x; i < npartial; i += blockDim.x) s += (double)partial[i];
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float
                                                    int64_t n_w1_4, int ld4, const int32_t* __restrict__ slot_of_item,
                                                    const float4* __restrict__ gs, const float4* __restrict__ gd,
                                                    const hvae_step_state* __restrict__ st, float wd, float b1, float b2, float eps) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 g;
@@ -123,6 +127,7 @@ __device__ __forceinline__ void philox(uint64_t seed, uint64_t ctr, uint32_t str
 
 __global__ void noise_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float keep, uint64_t seed, uint64_t offset, uint32_t sid,
                                   const hvae_step_state* __restrict__ st) {
+    pdl_prologue();
     const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 * 4 >= n) return;
     if (st) offset += ((uint64_t)st->noise_hi << 32 | st->noise_lo);
@@ -136,6 +141,7 @@ __global__ void noise_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float k
 
 __global__ void noise_normal_kernel(float* __restrict__ eps, int64_t n, uint64_t seed, uint64_t offset, uint32_t sid,
                                     const hvae_step_state* __restrict__ st) {
+    pdl_prologue();
     const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 * 4 >= n) return;
     if (st) offset += ((uint64_t)st->noise_hi << 32 | st->noise_lo);
@@ -162,7 +168,7 @@ extern "C" {
 int hvae_step_begin(hvae_step_state* state, double lr, double beta1, double beta2, double kl_beta_min, double kl_beta_max,
                     int anneal_steps, int b_global, int advance, uint32_t noise_stride, void* stream) {
     HVAE_REQUIRE(b_global > 0, "step_begin: global batch must be positive");
-    step_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2, kl_beta_min, kl_beta_max, anneal_steps, b_global, advance,
+    launch_pdl(step_begin_kernel, 1, 1, 0, (cudaStream_t)stream, state, lr, beta1, beta2, kl_beta_min, kl_beta_max, anneal_steps, b_global, advance,
                                                          noise_stride);
     HVAE_LAUNCH_CHECK("step_begin");
     return 0;
@@ -172,8 +178,8 @@ int hvae_step_begin(hvae_step_state* state, double lr, double beta1, double beta
 int hvae_grad_norm_clip(const float* gdense, int64_t n_dense, const float* rownorm2, const int32_t* n_unique, float max_norm,
                         hvae_step_state* state, float* workspace, void* stream) {
     const int blocks = (int)max((int64_t)1, min((int64_t)kNumSMs, (n_dense + 255) / 256));
-    sumsq_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gdense, n_dense, workspace);
-    gradnorm_final_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(workspace, blocks, rownorm2, n_unique, max_norm, state);
+    launch_pdl(sumsq_partial_kernel, blocks, 256, 0, (cudaStream_t)stream, gdense, n_dense, workspace);
+    launch_pdl(gradnorm_final_kernel, 1, 1024, 0, (cudaStream_t)stream, workspace, blocks, rownorm2, n_unique, max_norm, state);
     HVAE_LAUNCH_CHECK("grad_norm_clip");
     return 0;
 }
@@ -184,7 +190,7 @@ int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_p
     HVAE_REQUIRE(n_params % 4 == 0 && n_w1 % 4 == 0 && ld1 % 4 == 0, "adam_step: sizes must be multiples of 4");
     if (n_params == 0) return 0;
     const int64_t n4 = n_params / 4;
-    adam_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(adam_kernel, (unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream, 
         (float4*)params, (float4*)exp_avg, (float4*)exp_avg_sq, n4, n_w1 / 4, ld1 / 4, slot_of_item, (const float4*)gsparse,
         (const float4*)gdense, state, weight_decay, beta1, beta2, eps);
     HVAE_LAUNCH_CHECK("adam_step");
@@ -194,10 +200,10 @@ int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_p
 int hvae_fill_noise(uint8_t* mask, int64_t n_mask, float keep_prob, float* eps, int64_t n_eps, uint64_t seed, uint64_t offset,
                     uint32_t stream_id, const hvae_step_state* state, void* stream) {
     if (mask && n_mask > 0)
-        noise_mask_kernel<<<(unsigned)((n_mask / 4 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(mask, n_mask, keep_prob, seed, offset, stream_id,
+        launch_pdl(noise_mask_kernel, (unsigned)((n_mask / 4 + 256) / 256), 256, 0, (cudaStream_t)stream, mask, n_mask, keep_prob, seed, offset, stream_id,
                                                                                                   state);
     if (eps && n_eps > 0)
-        noise_normal_kernel<<<(unsigned)((n_eps / 4 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(eps, n_eps, seed, offset,
+        launch_pdl(noise_normal_kernel, (unsigned)((n_eps / 4 + 256) / 256), 256, 0, (cudaStream_t)stream, eps, n_eps, seed, offset,
                                                                                                     stream_id + 0x80000000u, state);
     HVAE_LAUNCH_CHECK("fill_noise");
     return 0;

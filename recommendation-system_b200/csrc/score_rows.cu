@@ -21,6 +21,7 @@ __device__ __forceinline__ void ml_merge(float& m, float& l, float m2, float l2)
 }
 
 __global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ S, int64_t lds, int N, float* __restrict__ lse) {
+    pdl_prologue();
     const float* row = S + (size_t)blockIdx.x * lds;
     float m = -INFINITY, l = 0.f;
     for (int i = threadIdx.x; i < N; i += 256) {
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ 
 // P = exp(S - lse_b) * xsum_b * inv_bg  in place
 __global__ void row_softmax_scale_kernel(float* __restrict__ S, int64_t lds, int rows, int N, const float* __restrict__ lse,
                                          const float* __restrict__ xsum, const float* __restrict__ inv_bg) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)rows * N) return;
     const int r = (int)(i / N), c = (int)(i - (int64_t)r * N);
@@ -60,6 +62,7 @@ __global__ void __launch_bounds__(256) sparse_dot_xsum_kernel(const int64_t* __r
                                                               const float* __restrict__ values, const int32_t* __restrict__ rows,
                                                               int B, const T* __restrict__ U, int ldu, const T* __restrict__ E,
                                                               int lde, int d, float* __restrict__ dot, float* __restrict__ xsum) {
+    pdl_prologue();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     const int u = rows ? rows[b] : b;
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restr
                                                           const float* __restrict__ O, int ldo, int n_parts,
                                                           const float* __restrict__ oscale, const T* __restrict__ E, int lde, int d,
                                                           const float* __restrict__ inv_bg, float* __restrict__ dU, int lddu) {
+    pdl_prologue();
     const int ld4 = lddu >> 2;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * ld4) return;
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(256) sparse_dot_xsum_bf16_kernel(const int64_t
                                                                    int B, const __nv_bfloat16* __restrict__ U, int ldu,
                                                                    const __nv_bfloat16* __restrict__ E, int lde, int nchunks,
                                                                    float* __restrict__ dot, float* __restrict__ xsum) {
+    pdl_prologue();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     const int u = rows ? rows[b] : b;
@@ -185,6 +190,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) candidate_rank_kernel(const T* __restrict__ U, int ldu, const T* __restrict__ E, int lde, int d,
                                                              const int32_t* __restrict__ cand, int C, int B, float* __restrict__ scores,
                                                              int32_t* __restrict__ rank) {
+    pdl_prologue();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     float s0 = 0.f;
@@ -232,6 +238,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32) mask_topk_kernel(float* __res
                                                                     const int32_t* __restrict__ indices,
                                                                     const int32_t* __restrict__ rows, int exclude_seen, int K,
                                                                     float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+    pdl_prologue();
     __shared__ float sv_all[kTopkWarps][kMaxK];
     __shared__ int si_all[kTopkWarps][kMaxK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -279,6 +286,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32) mask_topk_kernel(float* __res
 __global__ void __launch_bounds__(kTopkWarps * 32) topk_merge_kernel(const float* __restrict__ cval, const int32_t* __restrict__ cidx,
                                                                      int n_rows, int GK, int K, float* __restrict__ out_val,
                                                                      int32_t* __restrict__ out_idx) {
+    pdl_prologue();
     __shared__ float sv_all[kTopkWarps][kMaxK];
     __shared__ int si_all[kTopkWarps][kMaxK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -303,6 +311,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_merge_kernel(const float
 // hit mask: bit p of mask[r] (4 x u32 per row) is set iff topk[r][p] is one of the row's relevant items.
 __global__ void hit_mask_kernel(const int32_t* __restrict__ topk, int n_rows, int K, const int64_t* __restrict__ rel_ptr,
                                 const int32_t* __restrict__ rel_idx, uint32_t* __restrict__ mask) {
+    pdl_prologue();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= n_rows) return;
     const int64_t s = rel_ptr[r], e = rel_ptr[r + 1];
@@ -325,6 +334,7 @@ __global__ void __launch_bounds__(256) metrics_partial_kernel(const uint32_t* __
                                                               int n_rows, const int32_t* __restrict__ kvals, int nk,
                                                               const double* __restrict__ disc, const double* __restrict__ idcg,
                                                               double* __restrict__ sums) {
+    pdl_prologue();
     __shared__ double red[8][25];
     double acc[25];
     for (int i = 0; i < 25; ++i) acc[i] = 0.0;
@@ -359,6 +369,7 @@ __global__ void __launch_bounds__(256) metrics_partial_kernel(const uint32_t* __
 }
 
 __global__ void metrics_final_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out) {
+    pdl_prologue();
     const int i = threadIdx.x;
     if (i >= nv) return;
     double v = 0.0;
@@ -374,7 +385,7 @@ extern "C" {
 
 int hvae_row_lse(const float* S, int64_t lds, int rows, int N, float* lse, void* stream) {
     if (rows == 0) return 0;
-    row_lse_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(S, lds, N, lse);
+    launch_pdl(row_lse_kernel, rows, 256, 0, (cudaStream_t)stream, S, lds, N, lse);
     HVAE_LAUNCH_CHECK("row_lse");
     return 0;
 }
@@ -383,7 +394,7 @@ int hvae_row_softmax_scale(float* S, int64_t lds, int rows, int N, const float* 
                            void* stream) {
     if (rows == 0) return 0;
     const int64_t total = (int64_t)rows * N;
-    row_softmax_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(S, lds, rows, N, lse, xsum, inv_bg);
+    launch_pdl(row_softmax_scale_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, S, lds, rows, N, lse, xsum, inv_bg);
     HVAE_LAUNCH_CHECK("row_softmax_scale");
     return 0;
 }
@@ -392,13 +403,13 @@ int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const fl
                          const void* U, int ldu, const void* E, int lde, int d, int is_bf16, float* dot, float* xsum, void* stream) {
     if (B == 0) return 0;
     if (is_bf16 && ldu % 8 == 0 && lde % 8 == 0 && d <= 1024)
-        sparse_dot_xsum_bf16_kernel<<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
+        launch_pdl(sparse_dot_xsum_bf16_kernel, ceil_div(B, 8), 256, 0, (cudaStream_t)stream, 
             indptr, indices, values, rows, B, (const __nv_bfloat16*)U, ldu, (const __nv_bfloat16*)E, lde, ceil_div(d, 8), dot, xsum);
     else if (is_bf16)
-        sparse_dot_xsum_kernel<__nv_bfloat16><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(
+        launch_pdl(sparse_dot_xsum_kernel<__nv_bfloat16>, ceil_div(B, 8), 256, 0, (cudaStream_t)stream, 
             indptr, indices, values, rows, B, (const __nv_bfloat16*)U, ldu, (const __nv_bfloat16*)E, lde, d, dot, xsum);
     else
-        sparse_dot_xsum_kernel<float><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, (const float*)U,
+        launch_pdl(sparse_dot_xsum_kernel<float>, ceil_div(B, 8), 256, 0, (cudaStream_t)stream, indptr, indices, values, rows, B, (const float*)U,
                                                                                        ldu, (const float*)E, lde, d, dot, xsum);
     HVAE_LAUNCH_CHECK("sparse_dot_xsum");
     return 0;
@@ -411,10 +422,10 @@ int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float*
     HVAE_REQUIRE(lddu % 4 == 0 && ldo % 4 == 0 && (!is_bf16 || lde % 8 == 0), "du_finalize: leading dimensions must be multiples of 4 (bf16 E: 8)");
     const int nb = ceil_div(B * (lddu / 4), 256);
     if (is_bf16)
-        du_finalize_kernel<__nv_bfloat16><<<nb, 256, 0, (cudaStream_t)stream>>>(
+        launch_pdl(du_finalize_kernel<__nv_bfloat16>, nb, 256, 0, (cudaStream_t)stream, 
             indptr, indices, values, rows, B, O, ldo, n_parts, oscale, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
     else
-        du_finalize_kernel<float><<<nb, 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
+        launch_pdl(du_finalize_kernel<float>, nb, 256, 0, (cudaStream_t)stream, indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
                                                                                    (const float*)E, lde, d, inv_bg, dU, lddu);
     HVAE_LAUNCH_CHECK("du_finalize");
     return 0;
@@ -425,10 +436,10 @@ int hvae_candidate_rank(const void* U, int ldu, const void* E, int lde, int d, i
     if (B == 0) return 0;
     HVAE_REQUIRE(C >= 1, "candidate_rank: need at least the test item");
     if (is_bf16)
-        candidate_rank_kernel<__nv_bfloat16><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)U, ldu, (const __nv_bfloat16*)E,
+        launch_pdl(candidate_rank_kernel<__nv_bfloat16>, ceil_div(B, 8), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)U, ldu, (const __nv_bfloat16*)E,
                                                                                                lde, d, cand, C, B, scores, rank);
     else
-        candidate_rank_kernel<float><<<ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>((const float*)U, ldu, (const float*)E, lde, d, cand, C, B,
+        launch_pdl(candidate_rank_kernel<float>, ceil_div(B, 8), 256, 0, (cudaStream_t)stream, (const float*)U, ldu, (const float*)E, lde, d, cand, C, B,
                                                                                        scores, rank);
     HVAE_LAUNCH_CHECK("candidate_rank");
     return 0;
@@ -438,7 +449,7 @@ int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, co
                    const int32_t* rows, int exclude_seen, int K, float* out_val, int32_t* out_idx, void* stream) {
     HVAE_REQUIRE(K >= 1 && K <= kMaxK, "mask_topk: K=%d outside [1,%d]", K, kMaxK);
     if (n_rows == 0) return 0;
-    mask_topk_kernel<<<ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream>>>(
+    launch_pdl(mask_topk_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, 
         S, lds, n_rows, N, item_offset, indptr, indices, rows, exclude_seen, K, out_val, out_idx);
     HVAE_LAUNCH_CHECK("mask_topk");
     return 0;
@@ -447,7 +458,7 @@ int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, co
 int hvae_topk_merge(const float* cval, const int32_t* cidx, int n_rows, int GK, int K, float* out_val, int32_t* out_idx, void* stream) {
     HVAE_REQUIRE(K >= 1 && K <= kMaxK, "topk_merge: K=%d outside [1,%d]", K, kMaxK);
     if (n_rows == 0) return 0;
-    topk_merge_kernel<<<ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream>>>(cval, cidx, n_rows, GK, K, out_val,
+    launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, cval, cidx, n_rows, GK, K, out_val,
                                                                                                   out_idx);
     HVAE_LAUNCH_CHECK("topk_merge");
     return 0;
@@ -456,7 +467,7 @@ int hvae_topk_merge(const float* cval, const int32_t* cidx, int n_rows, int GK, 
 int hvae_hit_mask(const int32_t* topk, int n_rows, int K, const int64_t* rel_ptr, const int32_t* rel_idx, uint32_t* mask, void* stream) {
     HVAE_REQUIRE(K >= 1 && K <= kMaxK, "hit_mask: K=%d outside [1,%d]", K, kMaxK);
     if (n_rows == 0) return 0;
-    hit_mask_kernel<<<ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(topk, n_rows, K, rel_ptr, rel_idx, mask);
+    launch_pdl(hit_mask_kernel, ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream, topk, n_rows, K, rel_ptr, rel_idx, mask);
     HVAE_LAUNCH_CHECK("hit_mask");
     return 0;
 }
@@ -466,8 +477,8 @@ int hvae_metrics_reduce(const uint32_t* mask, const int64_t* rel_ptr, int n_rows
                         const double* idcg, double* workspace, double* out, void* stream) {
     HVAE_REQUIRE(nk >= 1 && nk <= 8, "metrics_reduce: nk=%d outside [1,8]", nk);
     const int blocks = max(1, min(kNumSMs, ceil_div(n_rows, 256)));
-    metrics_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, rel_ptr, n_rows, kvals, nk, disc, idcg, workspace);
-    metrics_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, blocks, nk * 3 + 1, out);
+    launch_pdl(metrics_partial_kernel, blocks, 256, 0, (cudaStream_t)stream, mask, rel_ptr, n_rows, kvals, nk, disc, idcg, workspace);
+    launch_pdl(metrics_final_kernel, 1, 32, 0, (cudaStream_t)stream, workspace, blocks, nk * 3 + 1, out);
     HVAE_LAUNCH_CHECK("metrics_reduce");
     return 0;
 }

@@ -53,6 +53,7 @@ __device__ __forceinline__ bool better(float v, int i, float tv, int ti) { retur
 template <int MODE>
 __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_constant__ CUtensorMap tmU,
                                                              const __grid_constant__ CUtensorMap tmE, StatsParams P) {
+    pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + STAGES * STAGE_BYTES);
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
 
     if (warp == 0) {
         if (lane == 0) {
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
 // lse[b] = log sum_s l_s * exp(m_s - M) + M over the item splits
 __global__ void lse_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, int B, int n_splits,
                                  float* __restrict__ lse) {
+    pdl_prologue();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float M = -INFINITY;
@@ -263,6 +266,7 @@ __global__ void lse_merge_kernel(const float* __restrict__ part_m, const float* 
 // fp32 [rows, cols] (leading dim ld_src) -> bf16 [rows, ld_dst] with zero padding of columns cols..ld_dst
 __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, __nv_bfloat16* __restrict__ dst,
                                  int ld_dst) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)rows * ld_dst) return;
     const int r = (int)(i / ld_dst), c = (int)(i - (int64_t)r * ld_dst);
@@ -300,6 +304,7 @@ struct __align__(8) GradBarriers {
 
 __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constant__ CUtensorMap tmU,
                                                             const __grid_constant__ CUtensorMap tmE, GradParams P) {
+    pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* pbuf = smem + G_STAGES * G_SLOT;                         // 2 x 32 KB
@@ -329,6 +334,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
     const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
 
     if (warp == 0) {
@@ -559,7 +565,7 @@ extern "C" {
 int hvae_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, void* stream) {
     if (rows == 0) return 0;
     const int64_t total = (int64_t)rows * ld_dst;
-    cast_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld_src, (__nv_bfloat16*)dst, ld_dst);
+    launch_pdl(cast_bf16_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, src, rows, cols, ld_src, (__nv_bfloat16*)dst, ld_dst);
     HVAE_LAUNCH_CHECK("cast_bf16");
     return 0;
 }
@@ -583,7 +589,7 @@ static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int ld
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
         attr_set = true;
     }
-    score_stats_kernel<MODE_LSE><<<dim3(m_tiles, P.n_splits), 192, kStatsSmem, stream>>>(tmU, tmE, P);
+    launch_pdl(score_stats_kernel<MODE_LSE>, dim3(m_tiles, P.n_splits), 192, kStatsSmem, stream, tmU, tmE, P);
     HVAE_LAUNCH_CHECK("tc_score_lse");
     *n_splits = P.n_splits;
     return 0;
@@ -606,7 +612,7 @@ static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, in
         HVAE_CUDA(cudaFuncSetAttribute(score_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
         attr_set = true;
     }
-    score_grad_kernel<<<dim3(m_tiles, n_chunks, P.n_splits), 192, kGradSmem, stream>>>(tmU, tmE, P);
+    launch_pdl(score_grad_kernel, dim3(m_tiles, n_chunks, P.n_splits), 192, kGradSmem, stream, tmU, tmE, P);
     HVAE_LAUNCH_CHECK("tc_score_grad");
     return 0;
 }
@@ -617,7 +623,7 @@ int hvae_tc_score_lse(const void* U, int ldu, int B, const void* E, int lde, int
     HVAE_REQUIRE(N > 0 && d > 0, "tc_score_lse: empty catalogue");
     int ns = 0;
     if (int rc = launch_stats_lse(U, ldu, B, E, lde, N, d, workspace, &ns, (cudaStream_t)stream)) return rc;
-    lse_merge_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(workspace, workspace + (size_t)B * ns, B, ns, lse);
+    launch_pdl(lse_merge_kernel, ceil_div(B, 128), 128, 0, (cudaStream_t)stream, workspace, workspace + (size_t)B * ns, B, ns, lse);
     HVAE_LAUNCH_CHECK("tc_score_lse merge");
     return 0;
 }
@@ -653,7 +659,7 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
         attr_set = true;
     }
-    score_stats_kernel<MODE_TOPK><<<dim3(m_tiles, P.n_splits), 192, kStatsSmem, (cudaStream_t)stream>>>(tmU, tmE, P);
+    launch_pdl(score_stats_kernel<MODE_TOPK>, dim3(m_tiles, P.n_splits), 192, kStatsSmem, (cudaStream_t)stream, tmU, tmE, P);
     HVAE_LAUNCH_CHECK("tc_score_topk");
     return 0;
 }
