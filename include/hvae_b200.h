@@ -150,8 +150,9 @@ size_t hvae_tc_n_splits(int B, int N);
 /* lse[b] = log sum_i exp(S_bi).  workspace >= 2 * B * hvae_tc_n_splits(B,N) floats. */
 int hvae_tc_score_lse(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* lse, float* workspace,
                       void* stream);
+size_t hvae_tc_topk_splits(int B, int N);
 /* per item split, the K best (score, global item id) of every user with the user's seen items excluded
- * (indptr == NULL: nothing excluded).  cand_val / cand_idx: [B, hvae_tc_n_splits(B,N) * K]; reduce with
+ * (indptr == NULL: nothing excluded).  cand_val / cand_idx: [B, hvae_tc_topk_splits(B,N) * K]; reduce with
  * hvae_topk_merge.  K <= 32.  E points at the first item of the shard, item_offset is its global id. */
 int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, int N, int d, int item_offset,
                        const int64_t* indptr, const int32_t* indices, const int32_t* rows, int K, float* cand_val,

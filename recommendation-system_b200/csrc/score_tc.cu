@@ -551,6 +551,13 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int l
 }
 
 static int pick_splits(int m_tiles, int n_tiles) { return pick_wave_splits(m_tiles, n_tiles); }
+// Top-K mode: every item split restarts its per-row candidate list, and a list costs ~K(1 + ln(items/K)) insertions per
+// row, so the epilogue work grows with the number of splits: use a single wave of CTAs (at most one CTA per SM).
+static int pick_topk_splits(int m_tiles, int n_tiles) {
+    const int splits = max(1, min(n_tiles, kNumSMs / max(1, m_tiles)));
+    const int tps = (n_tiles + splits - 1) / splits;
+    return (n_tiles + tps - 1) / tps;
+}
 
 constexpr size_t kStatsSmem = STAGES * STAGE_BYTES + 256 + BM * (MAXK_TC + 1) * 8 + 1024;
 
@@ -571,6 +578,7 @@ int hvae_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, 
 }
 
 size_t hvae_tc_n_splits(int B, int N) { return (size_t)pick_splits(ceil_div(B, BM), ceil_div(N, BN)); }
+size_t hvae_tc_topk_splits(int B, int N) { return (size_t)pick_topk_splits(ceil_div(B, BM), ceil_div(N, BN)); }
 
 static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* workspace, int* n_splits,
                             cudaStream_t stream) {
@@ -650,7 +658,7 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
     const int m_tiles = ceil_div(B, BM), n_tiles = ceil_div(N, BN);
     StatsParams P{};
     P.B = B; P.N = N; P.d = d; P.K = K; P.item_offset = item_offset;
-    P.n_splits = pick_splits(m_tiles, n_tiles);
+    P.n_splits = pick_topk_splits(m_tiles, n_tiles);
     P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
     P.cand_val = cand_val; P.cand_idx = cand_idx;
     P.indptr = indptr; P.indices = indices; P.rows = rows;

@@ -63,7 +63,7 @@ def topk_bf16(eng, batch, u, K, exclude_seen, item_lo, item_hi, out_val, out_idx
     n_it = item_hi - item_lo
     Eb = eng.E_bf16
     ub = user_vectors_bf16(eng, u, B)
-    ns = int(lib.tc_n_splits(B, n_it))
+    ns = int(lib.tc_topk_splits(B, n_it))
     cv = ws.get("tc_cand_v", (B, ns * K))
     ci = ws.get("tc_cand_i", (B, ns * K), torch.int32)
     csr = batch.csr

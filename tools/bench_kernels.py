@@ -39,8 +39,9 @@ def main():
     gs = int(lib.tc_grad_splits(B, N, d))
     ldo = (d + 3) // 4 * 4
     Op = torch.empty(gs, B, ldo, device=dev)
-    cv = torch.empty(B, ns * K, device=dev)
-    ci = torch.empty(B, ns * K, dtype=torch.int32, device=dev)
+    nst = int(lib.tc_topk_splits(B, N))
+    cv = torch.empty(B, nst * K, device=dev)
+    ci = torch.empty(B, nst * K, dtype=torch.int32, device=dev)
     indptr = torch.arange(0, 10 * (B + 1), 10, dtype=torch.int64, device=dev)
     indices = torch.sort(torch.randint(0, N, (B, 10), device=dev, generator=g), dim=1)[0].to(torch.int32).reshape(-1).contiguous()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
