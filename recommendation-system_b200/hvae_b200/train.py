@@ -451,6 +451,22 @@ class VAETrainer:
             logger.info("Saved best model to %s", best_path)
 
 
+def resume_from_checkpoint(trainer: "VAETrainer", path) -> int:
+    """Restore model weights, Adam moments / step count, loss histories and the annealing step from a checkpoint written by
+    save_checkpoint (the reference saves optimizer_state_dict but never reloads it).  Returns the epoch."""
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    trainer.model.load_state_dict(ck["model_state_dict"])
+    trainer.model.to(trainer.device)
+    if ck.get("optimizer_state_dict", {}).get("state"):
+        trainer.optimizer.load_state_dict(ck["optimizer_state_dict"])
+    for k in ("train_losses", "val_losses", "train_recon_losses", "train_kl_losses"):
+        setattr(trainer, k, list(ck.get(k, [])))
+    if hasattr(trainer.model, "current_step") and "annealing_current_step" in ck:
+        trainer.model.current_step = int(ck["annealing_current_step"])
+    trainer._graphs.clear()
+    return int(ck.get("epoch", 0))
+
+
 def _get_device(device: str | None = None) -> torch.device:
     if device:
         return torch.device(device)

@@ -391,3 +391,98 @@ def test_negative_sampling_eval_matches_oracle(dev):
     res = ev.evaluate_dataset_with_negatives(test_df, 99, [5, 10], seed=5)
     assert set(res) == {5, 10} and 0.0 <= res[10]["ndcg"] <= res[10]["hit_ratio"] <= 1.0
     assert res[5]["hit_ratio"] <= res[10]["hit_ratio"]
+
+
+def test_resume_continues_bit_identically(dev, tmp_path):
+    """save_checkpoint -> resume_from_checkpoint restores weights, Adam state and the annealing step: the continued run
+    equals the uninterrupted one."""
+    from hvae_b200.train import CSRLoader, VAETrainer, resume_from_checkpoint
+    c = Case("tiny_annealed")
+    def fresh():
+        torch.manual_seed(3)
+        m = _build(c, dev, precision="fp32")
+        tr = VAETrainer(m, dev, lr=1e-3, use_cuda_graph=False)
+        tr._noise_seed = 99
+        return m, tr
+    ld = lambda: CSRLoader(c.csr, list(range(96)), 32, False, dev)
+    m1, t1 = fresh()
+    for _ in range(2):
+        t1.train_epoch(ld())
+    t1.save_checkpoint(tmp_path / "ck.pth", 2)
+    ref = t1.train_epoch(ld())
+    m2, t2 = fresh()
+    assert resume_from_checkpoint(t2, tmp_path / "ck.pth") == 2
+    # the in-kernel noise counter is part of the device step state, not of the checkpoint: carry it over for the comparison
+    m2.engine.ensure_optimizer()
+    st1 = m1.engine.read_state()
+    assert m2.current_step == 6 and int(m2.engine.read_state()["adam_step"]) == 6
+    off = m2.engine.state.view(torch.int32)
+    from hvae_b200._cabi import STATE_OFF
+    off[STATE_OFF["noise_lo"]] = int(6 * t1._noise_stride(32)) & 0x7FFFFFFF
+    got = t2.train_epoch(ld())
+    assert got == ref
+    for k, v in m1.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k]), k
+
+
+def test_bf16_large_k_and_recommend(dev):
+    """K beyond the fused epilogue (API top_k <= 100, src/api/schemas.py:8) falls back to the materialised path; recommend()."""
+    from hvae_b200.evaluate import RecommendationEvaluator
+    c = Case("tiny_two_hidden")
+    m = _build(c, dev, precision="bf16", state="final")
+    ev = RecommendationEvaluator(m, c.csr, {}, {}, dev)
+    i100, s100 = ev.get_user_recommendations(3, top_k=100)
+    i20, s20 = ev.get_user_recommendations(3, top_k=20)
+    assert len(i100) == 100 and np.all(np.diff(s100[np.isfinite(s100)]) <= 1e-6)
+    assert len(set(i20.tolist()) & set(i100[:25].tolist())) >= 18          # bf16 vs fp32 scoring: same head of the ranking
+    seen = set(c.csr[3].indices.tolist())
+    assert not (set(i100[np.isfinite(s100)].tolist()) & seen)
+    m.eval()
+    mu = m.get_user_embedding(c.dense(np.arange(4)).to(dev))
+    idx, val = m.recommend(mu, top_k=7)
+    assert idx.shape == (4, 7) and torch.all(val[:, :-1] >= val[:, 1:])
+
+
+def test_c2_scale_properties(dev):
+    """BASELINE configs[1] at full size (22,363 x 12,101, d=384): size-independent properties instead of an oracle run --
+    the tensor-core log-sum-exp equals the materialised fp32 one, softmax-weighted sums are convex combinations of E rows,
+    bf16 and fp32 training agree on the loss, top-K never returns a seen item and matches the fp32 ranking."""
+    from hvae_b200.engine import Batch, DeviceCSR
+    from hvae_b200.evaluate import RecommendationEvaluator
+    from hvae_b200.model import HybridVAE
+    from hvae_b200.synth import CONFIGS, make_interactions, make_item_embeddings
+    from hvae_b200.train import VAETrainer
+    cfg = CONFIGS["c2"]
+    data = make_interactions(cfg["n_users"], cfg["n_items"], 0)
+    E = make_item_embeddings(cfg["n_items"], cfg["emb_dim"], 0)
+    csr = DeviceCSR.from_arrays(data.indptr, data.indices, None, cfg["n_items"], dev)
+    losses = {}
+    models = {}
+    for prec in ("fp32", "bf16"):
+        torch.manual_seed(0)
+        m = HybridVAE(cfg["n_items"], E, cfg["latent_dim"], cfg["hidden_dims"], cfg["dropout"], cfg["beta"], precision=prec).to(dev)
+        tr = VAETrainer(m, dev, use_cuda_graph=(prec == "bf16"))
+        tr._noise_seed = 7
+        m.train()
+        out = []
+        for s in range(4):
+            rows = torch.arange(s * 512, (s + 1) * 512, dtype=torch.int32, device=dev)
+            tr.train_step(Batch(csr, rows, 512, int(data.indptr[(s + 1) * 512] - data.indptr[s * 512])))
+            out.append(tr.last_losses())
+        losses[prec], models[prec] = np.array(out), m
+    assert np.all(np.isfinite(losses["bf16"]))
+    np.testing.assert_allclose(losses["bf16"], losses["fp32"], rtol=1e-3)
+    # evaluation over every user: no seen item, ranking agrees with fp32 on the same (fp32-trained) weights
+    models["bf16"].load_state_dict(models["fp32"].state_dict())
+    users = np.arange(cfg["n_users"])
+    tops = {}
+    for prec in ("fp32", "bf16"):
+        ev = RecommendationEvaluator(models[prec], csr, {}, {}, dev)
+        _, idx = ev.topk_users(users, 10)
+        tops[prec] = idx.cpu().numpy()
+    seen_keys = set((np.repeat(users, np.diff(data.indptr)) * cfg["n_items"] + data.indices).tolist())
+    samp = np.random.default_rng(0).choice(cfg["n_users"], 500, replace=False)
+    for u in samp:
+        assert not any((u * cfg["n_items"] + int(i)) in seen_keys for i in tops["bf16"][u])
+    overlap = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(tops["fp32"], tops["bf16"])])
+    assert overlap > 0.97, overlap
