@@ -11,6 +11,7 @@
 //   warps 2..5  epilogue     : tcgen05.ld -> registers; thread <-> user row, so every reduction is thread-local
 // Roofline: tensor pipe (2*128*256*d flop per tile); HBM traffic is E once (L2 serves the re-reads across user tiles).
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "hvae_b200.h"
@@ -497,6 +498,223 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// d > 384: O needs two 384-column chunks (TMEM holds 384 O + 128 S columns), i.e. two CTAs per (user tile, item range).
+// Instead of both recomputing S for every item tile, they form a cluster of 2 and split the tiles: CTA r owns the tiles
+// with (tile & 1) == r -- it runs G1 and the softmax for them and writes the bf16 P tile into BOTH CTAs' shared memory
+// (local st.shared + st.shared::cluster through DSMEM, 32 KB per tile, ~5 B/cycle); both CTAs then run G2 for every tile
+// on their own column chunk.  Executed flops drop from 6*B*N*d to the algorithmic 4*B*N*d.
+// G2 lags two tiles behind G1 so that a tile's softmax (and the DSMEM copy) hides behind the two G2s in between.
+// P buffer b = tile & 1 is always written by CTA b: p_full[b] collects that CTA's four softmax warps (local or remote
+// arrives); p_free[b] lives in CTA b and collects the G2 completion of both CTAs (tcgen05.commit to a cluster address).
+__global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_constant__ CUtensorMap tmU,
+                                                                 const __grid_constant__ CUtensorMap tmE, GradParams P) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* pbuf = smem + G_STAGES * G_SLOT;                         // 2 x 32 KB
+    GradBarriers* bars = reinterpret_cast<GradBarriers*>(pbuf + 2 * G_PBYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, chunk = blockIdx.y, split = blockIdx.z;
+    const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;      // cluster = the two chunk CTAs: rank == chunk
+    const int n_tiles_total = (P.N + G_BN - 1) / G_BN;
+    const int t0 = split * P.tiles_per_split, t1 = min(n_tiles_total, t0 + P.tiles_per_split);
+    const int T = t1 - t0;
+    const int KB = (P.d + BK - 1) / BK;
+    const int dpad = KB * BK;
+    const int dc0 = chunk * G_DCHUNK;
+    const int DC = min(G_DCHUNK, dpad - dc0);
+    const int NG = (DC + 255) / 256;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmU);
+        tma_prefetch_desc(&tmE);
+        for (int s = 0; s < G_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        mbar_init(&bars->s_full, 1); mbar_init(&bars->s_free, 4); mbar_init(&bars->o_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars->p_full[a], 4); mbar_init(&bars->p_free[a], 2); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // the peer's barriers are initialised before anybody arrives on them remotely
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();
+    const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
+    auto own = [&](int ti) { return (uint32_t)(ti & 1) == rank; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            auto acquire = [&](uint32_t bytes) {
+                const int s = it % G_STAGES;
+                mbar_wait(&bars->empty[s], ((it / G_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&bars->full[s], bytes);
+                ++it;
+                return s;
+            };
+            for (int ti = 0; ti < T + 2; ++ti) {
+                if (ti < T && own(ti)) {          // G1 operands of my tile ti
+                    const int item0 = (t0 + ti) * G_BN;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const int s = acquire(G_SLOT);
+                        uint8_t* slot = smem + s * G_SLOT;
+                        tma_load_2d(slot, &tmU, kb * BK, m_tile * BM, &bars->full[s]);
+                        tma_load_2d(slot + 16384, &tmE, kb * BK, item0, &bars->full[s]);
+                        tma_load_2d(slot + 16384 + 8192, &tmE, kb * BK, item0 + 64, &bars->full[s]);
+                    }
+                }
+                if (ti >= 2) {                    // G2 operands of tile ti-2 (every tile, my column chunk)
+                    const int item0 = (t0 + ti - 2) * G_BN;
+                    for (int ih = 0; ih < 2; ++ih)
+                        for (int g = 0; g < NG; ++g) {
+                            const int nb = min(4, (DC - g * 256) / 64);
+                            const int s = acquire(nb * 8192);
+                            uint8_t* slot = smem + s * G_SLOT;
+                            for (int j = 0; j < nb; ++j)
+                                tma_load_2d(slot + j * 8192, &tmE, dc0 + g * 256 + j * 64, item0 + ih * 64, &bars->full[s]);
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = make_idesc(BM, G_BN, 0, 0);
+            int it = 0;
+            for (int ti = 0; ti < T + 2; ++ti) {
+                if (ti < T && own(ti)) {          // G1(ti): S = U E_t^T
+                    const int k = ti >> 1;        // my k-th own tile
+                    mbar_wait(&bars->s_free, (k & 1) ^ 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        const int s = it % G_STAGES;
+                        mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(smem + s * G_SLOT), b0 = a0 + 16384;
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; ++kk)
+                            umma_ss(tmem_S, make_desc(a0 + kk * 32, 16, 1024), make_desc(b0 + kk * 32, 16, 1024), idesc1, (kb | kk) != 0);
+                        umma_commit(&bars->empty[s]);
+                    }
+                    umma_commit(&bars->s_full);
+                }
+                if (ti >= 2) {                    // G2(ti-2): O += P E_t
+                    const int tj = ti - 2, pb = tj & 1;
+                    mbar_wait_cluster(&bars->p_full[pb], (tj >> 1) & 1);      // P may have been written by the peer CTA
+                    fence_proxy_async_all();
+                    tc_fence_after();
+                    const uint32_t p0 = smem_u32(pbuf + pb * G_PBYTES);
+                    for (int ih = 0; ih < 2; ++ih)
+                        for (int g = 0; g < NG; ++g, ++it) {
+                            const int ncols = min(256, DC - g * 256);
+                            const uint32_t idesc2 = make_idesc(BM, ncols, 0, 1);
+                            const int s = it % G_STAGES;
+                            mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t b0 = smem_u32(smem + s * G_SLOT);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_ss(tmem_O + g * 256, make_desc(p0 + ih * 16384 + kk * 32, 16, 1024),
+                                        make_desc(b0 + kk * 2048, 8192, 1024), idesc2, (tj | ih | kk) != 0);
+                            umma_commit(&bars->empty[s]);
+                        }
+                    // buffer pb may be rewritten once BOTH CTAs are done with it: its owner (CTA pb) collects both commits
+                    umma_commit_cluster(map_to_cta(smem_u32(&bars->p_free[pb]), (uint32_t)pb));
+                }
+            }
+            umma_commit(&bars->o_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int r_local = q * 32 + lane;
+        const int row = m_tile * BM + r_local;
+        const bool row_ok = row < P.B;
+        float lse_row = 0.f;
+        if (row_ok) {
+            if (P.lse) {
+                lse_row = P.lse[row];
+            } else {
+                const float* pm = P.part_m + (size_t)row * P.lse_splits;
+                const float* pl = P.part_l + (size_t)row * P.lse_splits;
+                float M = -INFINITY;
+                for (int sp = 0; sp < P.lse_splits; ++sp) M = fmaxf(M, pm[sp]);
+                float l = 0.f;
+                for (int sp = 0; sp < P.lse_splits; ++sp) l += pl[sp] * expf(pm[sp] - M);
+                lse_row = M + logf(l);
+                if (chunk == 0 && split == 0) P.lse_out[row] = lse_row;
+            }
+        }
+        const float lse2 = lse_row * kLog2e;
+        const uint32_t lane_base = uint32_t(q * 32) << 16;
+        const int pb = (int)rank;                                   // the buffer this CTA writes
+        const uint32_t pfull_local = smem_u32(&bars->p_full[pb]);
+        const uint32_t pfull_peer = map_to_cta(pfull_local, peer);
+        const uint32_t prow_local = smem_u32(pbuf + pb * G_PBYTES + r_local * 128);
+        const uint32_t prow_peer = map_to_cta(prow_local, peer);
+        for (int ti = (int)rank, k = 0; ti < T; ti += 2, ++k) {     // my tiles only
+            mbar_wait(&bars->s_full, k & 1);
+            tc_fence_after();
+            float v[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(tmem_S + lane_base + c * 32, v[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->s_free);
+            mbar_wait_cluster(&bars->p_free[pb], (k & 1) ^ 1);      // both CTAs finished G2 of my previous tile
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float p0 = exp2f(fmaf(v[c][j8 * 8 + 2 * e], kLog2e, -lse2));
+                        const float p1 = exp2f(fmaf(v[c][j8 * 8 + 2 * e + 1], kLog2e, -lse2));
+                        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+                        w[e] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    const int item = c * 32 + j8 * 8;
+                    const uint32_t off = (uint32_t)((item >> 6) * 16384 + ((((item & 63) >> 3) ^ (r_local & 7)) << 4));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_local + off), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                    st_cluster_v4(prow_peer + off, w[0], w[1], w[2], w[3]);
+                }
+            }
+            fence_proxy_async_all();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bars->p_full[pb]);
+                mbar_arrive_cluster(pfull_peer);
+            }
+        }
+        // ---- O (TMEM) -> global partial ---------------------------------------------------------------------
+        mbar_wait(&bars->o_full, 0);
+        tc_fence_after();
+        float* orow = P.Opart + ((size_t)split * P.B + row) * P.ldo + dc0;
+        for (int c = 0; c < DC / 32; ++c) {
+            float v[32];
+            tmem_ld32(tmem_O + lane_base + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (dc0 + c * 32 + j < P.ldo)
+                        *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // nobody leaves while the peer may still store into / arrive on this CTA's shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 constexpr size_t kGradSmem = G_STAGES * G_SLOT + 2 * G_PBYTES + 256 + 1024;
 
 // Item splits per (user tile, column chunk): one CTA per SM in a single wave when each CTA would otherwise get only a
@@ -618,7 +836,26 @@ static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, in
     static bool attr_set = false;
     if (!attr_set) {
         HVAE_CUDA(cudaFuncSetAttribute(score_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_grad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
         attr_set = true;
+    }
+    static const bool no_pair = getenv("HVAE_NO_PAIR") != nullptr;
+    if (n_chunks == 2 && !no_pair) {      // the two column-chunk CTAs share the softmax tiles through DSMEM (cluster of 2 along y)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(m_tiles, 2, P.n_splits);
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = kGradSmem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        HVAE_CUDA(cudaLaunchKernelEx(&cfg, score_grad_pair_kernel, tmU, tmE, P));
+        HVAE_LAUNCH_CHECK("tc_score_grad(pair)");
+        return 0;
     }
     launch_pdl(score_grad_kernel, dim3(m_tiles, n_chunks, P.n_splits), 192, kGradSmem, stream, tmU, tmE, P);
     HVAE_LAUNCH_CHECK("tc_score_grad");
