@@ -151,3 +151,23 @@ def test_negative_sampling_candidates():
             neg = cand[u, 1:1 + valid[u]].tolist()
             assert len(set(neg)) == len(neg) and not (set(neg) & seen) and d.test_items[u] not in neg
             assert valid[u] == min(99, N - len(seen) - 1)
+
+
+def test_torch_custom_ops_registered_and_cuda_only():
+    """torch.ops.hvae_b200.* exist, infer shapes on fake tensors, and refuse CPU tensors (no fallback)."""
+    import hvae_b200.ops  # noqa: F401  (registers the ops)
+    for name in ("gather_ln_fwd", "gemm", "score_lse", "score_grad", "score_topk", "adam_step"):
+        assert hasattr(torch.ops.hvae_b200, name), name
+    with pytest.raises(RuntimeError, match="CUDA"):
+        torch.ops.hvae_b200.score_lse(torch.zeros(4, 8, dtype=torch.bfloat16), torch.zeros(10, 8, dtype=torch.bfloat16), 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        torch.ops.hvae_b200.gemm(torch.zeros(4, 8), torch.zeros(6, 8), None, True)
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        U, E = torch.empty(5, 16, dtype=torch.bfloat16), torch.empty(40, 16, dtype=torch.bfloat16)
+        assert torch.ops.hvae_b200.score_lse(U, E, 12).shape == (5,)
+        assert torch.ops.hvae_b200.score_grad(U, E, torch.empty(5), 12).shape == (5, 12)
+        v, i = torch.ops.hvae_b200.score_topk(U, E, 12, torch.empty(6, dtype=torch.int64), torch.empty(9, dtype=torch.int32),
+                                              torch.empty(5, dtype=torch.int32), 7, 0)
+        assert v.shape == (5, 7) and i.dtype == torch.int32
+        assert torch.ops.hvae_b200.gemm(torch.empty(5, 16), torch.empty(9, 16), None, True).shape == (5, 9)

@@ -155,3 +155,56 @@ def test_gemm_tf32_all_layouts(dev):
                 assert np.isfinite(got).all(), (M, N, K, a_t, b_t)
                 assert np.abs(got - ref).max() < 2e-3 * scale, (M, N, K, a_t, b_t, np.abs(got - ref).max(), scale)   # TF32: 10-bit mantissa
                 assert torch.isnan(C[:, N:]).all()        # pad columns untouched
+
+
+def test_torch_custom_ops_match_plain_torch(dev):
+    """torch.ops.hvae_b200.*: the registered operators give the library's results."""
+    import hvae_b200.ops  # noqa: F401
+    from hvae_b200.synth import make_interactions
+    B, N, d, h = 200, 3000, 384, 600
+    U, E = _operands(B, N, d, dev, seed=5)
+    Ub, Eb = U.to(torch.bfloat16).contiguous(), E.to(torch.bfloat16).contiguous()
+    S = Ub.float().double() @ Eb.float().double().t()
+    lse = torch.ops.hvae_b200.score_lse(Ub, Eb, d)
+    np.testing.assert_allclose(lse.cpu().numpy(), torch.logsumexp(S, 1).cpu().numpy(), rtol=2e-6, atol=2e-5)
+    O = torch.ops.hvae_b200.score_grad(Ub, Eb, lse, d)
+    ref = torch.softmax(S, 1) @ Eb.float().double()
+    assert float((O.double() - ref).abs().max()) < 1e-2 * float(ref.abs().max())
+    data = make_interactions(B, N, 1)
+    indptr, indices = torch.from_numpy(data.indptr).to(dev), torch.from_numpy(data.indices).to(dev)
+    rows = torch.arange(B, dtype=torch.int32, device=dev)
+    val, idx = torch.ops.hvae_b200.score_topk(Ub, Eb, d, indptr, indices, rows, 10, 0)
+    Sm = S.float().clone()
+    Sm[torch.from_numpy(np.repeat(np.arange(B), np.diff(data.indptr))).to(dev), indices.long()] = -float("inf")
+    np.testing.assert_allclose(val.cpu().numpy(), torch.topk(Sm, 10, dim=1)[0].cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # encoder layer 1 and an MLP GEMM
+    g = torch.Generator().manual_seed(0)
+    W1T = torch.randn(N, h, generator=g).to(dev)
+    b1, gam, bet = torch.randn(h, generator=g).to(dev), torch.rand(h, generator=g).to(dev) + 0.5, torch.randn(h, generator=g).to(dev)
+    act = torch.ops.hvae_b200.gather_ln_fwd(indptr, indices, rows, W1T, b1, gam, bet, h)
+    from scipy.sparse import csr_matrix
+    X = torch.from_numpy(csr_matrix((np.ones(len(data.indices), np.float32), data.indices, data.indptr), shape=(B, N)).toarray()).to(dev)
+    ref_act = torch.nn.functional.gelu(torch.nn.functional.layer_norm(X @ W1T + b1, (h,), gam, bet, 1e-5))
+    np.testing.assert_allclose(act.cpu().numpy(), ref_act.cpu().numpy(), rtol=2e-4, atol=2e-4)
+    Wm = torch.randn(400, h, generator=g).to(dev)
+    bm = torch.randn(400, generator=g).to(dev)
+    out = torch.ops.hvae_b200.gemm(act, Wm, bm, True)
+    ref_out = act.double() @ Wm.double().t() + bm.double()
+    assert float((out.double() - ref_out).abs().max()) < 2e-3 * float(ref_out.abs().max())
+    # Adam on a flat arena: one step equals torch.optim.Adam
+    from hvae_b200._cabi import STATE_WORDS, p
+    from hvae_b200 import _cabi
+    prm = torch.randn(1024, generator=g).to(dev)
+    grad = torch.randn(1024, generator=g).to(dev)
+    ref_p = prm.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    ref_p.grad = grad.clone()
+    opt.step()
+    m, v = torch.zeros_like(prm), torch.zeros_like(prm)
+    state = torch.zeros(STATE_WORDS, device=dev)
+    lib = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    lib.step_begin(p(state), 1e-3, 0.9, 0.999, 0.0, 0.2, 0, 1, 1, 0, st)
+    lib.grad_norm_clip(p(grad), 1024, None, None, 1e30, p(state), p(torch.empty(256, device=dev)), st)
+    torch.ops.hvae_b200.adam_step(prm, m, v, grad, state, 0.0, 0.9, 0.999, 1e-8)
+    np.testing.assert_allclose(prm.cpu().numpy(), ref_p.detach().cpu().numpy(), rtol=1e-6, atol=1e-7)

@@ -8,7 +8,8 @@ import torch
 from hvae_b200 import _cabi
 lib = _cabi.lib(); dev = torch.device("cuda:0"); st = torch.cuda.current_stream().cuda_stream
 r4 = lambda n: (n + 3) // 4 * 4
-shapes = {"K32     [512x400,K32 ] NT": (512, 400, 32, False, True), "K128    [512x400,K128] NT": (512, 400, 128, False, True),
+shapes = {"K640al  [512x400,K640] NT": (512, 400, 640, False, True), "K608    [512x400,K608] NT": (512, 400, 608, False, True),
+          "K32     [512x400,K32 ] NT": (512, 400, 32, False, True), "K128    [512x400,K128] NT": (512, 400, 128, False, True),
           "K256    [512x400,K256] NT": (512, 400, 256, False, True), "K1200   [512x400,K1200] NT": (512, 400, 1200, False, True),
           "big     [4096x640,K600] NT": (4096, 640, 600, False, True),
           "fwd ml  [512x400,K600] NT": (512, 400, 600, False, True), "dX      [512x600,K400] NN": (512, 600, 400, False, False),
