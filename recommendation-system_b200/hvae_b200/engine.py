@@ -253,13 +253,13 @@ class Engine:
         self._forked.add(i)
         return torch.cuda.stream(st)
 
-    def join(self):
-        """Main stream waits for every side stream used since the last join."""
+    def join(self, only=None):
+        """Main stream waits for every side stream used since the last join (or just for the streams in `only`)."""
         if self._forked:
             cur = torch.cuda.current_stream(self.dev)
-            for i in sorted(self._forked):
+            for i in sorted(self._forked if only is None else self._forked & set(only)):
                 cur.wait_stream(self._side[i])
-            self._forked.clear()
+                self._forked.discard(i)
 
     def span_ms(self):
         """{name: [ms per occurrence]} of the recorded spans (synchronises)."""
@@ -421,14 +421,17 @@ class Engine:
     def forward_loss(self, batch: Batch, noise=None, want_grad=False, accumulate=True):
         """Forward + loss.  noise = dict(masks=[uint8 [B,h_i]...], eps=f32 [B,L], pmask=uint8 [B,d]) or None."""
         masks = None if noise is None else noise["masks"]
+        self.join(only=(3,))            # hidden-layer dropout masks (generated on a side stream by the trainer)
         ml = self.encode(batch, masks)
+        self.join(only=(4, 5))          # eps, projection dropout mask
         u = self.latent_and_project(batch.B, ml, None if noise is None else noise["eps"],
                                     None if noise is None else noise.get("pmask"))
         with self.span("score"):
             lse, dot, xsum, O, oscale = self.score_loss(batch, u, want_grad)
         self.join()
-        self.lib.loss_finalize(p(lse), p(dot), p(xsum), p(self.ws.get("kl_row", (batch.B,))), batch.B, self.state_ptr("inv_bg"),
-                               self.state_ptr("beta_kl"), p(self.loss_out), p(self.acc) if accumulate else None, self.stream)
+        with self.side(1):          # nothing downstream of the loss scalars inside the step: off the critical path
+            self.lib.loss_finalize(p(lse), p(dot), p(xsum), p(self.ws.get("kl_row", (batch.B,))), batch.B, self.state_ptr("inv_bg"),
+                                   self.state_ptr("beta_kl"), p(self.loss_out), p(self.acc) if accumulate else None, self.stream)
         return ml, u, O, oscale
 
     def backward(self, batch: Batch, noise, ml, O, oscale, dense_w1=None, ext_dml=None, du_override=None):
@@ -560,13 +563,14 @@ class Engine:
         return gs, rn2, tb["n_unique"], tb["uniq"]
 
     def train_step(self, batch: Batch, noise, lr=1e-3, weight_decay=0.0, beta_min=0.0, beta_max=0.2, anneal_steps=0,
-                   b_global=None, noise_stride=0):
+                   b_global=None, noise_stride=0, begun=False):
         """zero_grad + forward + loss + backward + clip_grad_norm_(5) + Adam (src/ml/train.py:88-92), fused."""
         self.ensure_optimizer()
         lib, st, lay = self.lib, self.stream, self.lay
         b_global = batch.B if b_global is None else b_global
         self.b_global = b_global
-        self.begin(b_global, lr, beta_min, beta_max, anneal_steps, advance=True, noise_stride=noise_stride)
+        if not begun:      # (the trainer calls begin() itself before it forks the noise kernels onto side streams)
+            self.begin(b_global, lr, beta_min, beta_max, anneal_steps, advance=True, noise_stride=noise_stride)
         # the item-major view of the (global) batch does not depend on the forward pass: side stream
         with self.side(2), self.span("transpose"):
             wbatch = batch if self.dist is None else self.dist.gather_batch(self, batch)

@@ -219,16 +219,19 @@ class VAETrainer:
         for i, h in enumerate(m.hidden_dims):
             if m.dropout > 0:
                 mk = eng.ws.get(f"mask{i}", (B, h), torch.uint8)
-                eng.lib.fill_noise(p(mk), B * h, keep, None, 0, seed, 0, 1 + i, stp, eng.stream)
+                with eng.side(3):
+                    eng.lib.fill_noise(p(mk), B * h, keep, None, 0, seed, 0, 1 + i, stp, eng.stream)
                 masks.append(mk)
             else:
                 masks.append(None)
         eps = eng.ws.get("eps", (B, m.latent_dim))
-        eng.lib.fill_noise(None, 0, keep, p(eps), B * m.latent_dim, seed, 0, 100, stp, eng.stream)
+        with eng.side(4):
+            eng.lib.fill_noise(None, 0, keep, p(eps), B * m.latent_dim, seed, 0, 100, stp, eng.stream)
         pmask = None
         if not lay.identity_proj and m.dropout > 0:
             pmask = eng.ws.get("pmask", (B, m.embedding_dim), torch.uint8)
-            eng.lib.fill_noise(p(pmask), B * m.embedding_dim, keep, None, 0, seed, 0, 200, stp, eng.stream)
+            with eng.side(5):
+                eng.lib.fill_noise(p(pmask), B * m.embedding_dim, keep, None, 0, seed, 0, 200, stp, eng.stream)
         return dict(masks=masks, eps=eps, pmask=pmask)
 
     # -- steps ---------------------------------------------------------------------------------------------------
@@ -248,11 +251,14 @@ class VAETrainer:
 
     def _eager_step(self, batch: Batch, noise, b_global):
         eng = self.model.engine
-        own_noise = noise is None
-        if own_noise:
-            noise = self._noise(batch.B)
-        eng.train_step(batch, noise, lr=self.lr, weight_decay=self.weight_decay, b_global=b_global,
-                       noise_stride=self._noise_stride(batch.B) if own_noise else 0, **self._anneal())
+        if noise is not None:       # injected noise (parity tests): nothing to generate
+            eng.train_step(batch, noise, lr=self.lr, weight_decay=self.weight_decay, b_global=b_global, **self._anneal())
+            return
+        # step scalars first (advances the device-side noise counter), then the noise kernels fork onto side streams
+        bg = batch.B if b_global is None else b_global
+        eng.begin(bg, self.lr, advance=True, noise_stride=self._noise_stride(batch.B), **self._anneal())
+        noise = self._noise(batch.B)
+        eng.train_step(batch, noise, lr=self.lr, weight_decay=self.weight_decay, b_global=b_global, begun=True, **self._anneal())
 
     def _graph_entry(self, kind, batch: Batch, b_global):
         """Static input buffers + captured graph of one step for this (batch size, nnz bound)."""
