@@ -67,18 +67,19 @@ int hvae_ln_act_bwd(const float* dact, const float* pre, const float* mean, cons
 int hvae_colsum(const float* X, int ld, int R, int C, float* out, float* workspace, void* stream);
 /* d(W1^T) for the touched rows only (replaces the dense dW1 = dH^T X of autograd). */
 /* Work plan: the touched items' entry lists are cut into work items of <= 64 entries (item popularity is heavy-tailed).
- * chunk_base, part_base: int32 [max_slots+1]; work_slot: int32 [hvae_w1_max_work(max_slots)]; n_work: int32 [1]. */
+ * chunk_base, part_base: int32 [max_slots+1]; work_slot: int32 [hvae_w1_max_work(max_slots)]; multi_slot: int32
+ * [hvae_w1_max_partial_rows(max_slots)] (slots with several chunks); n_work: int32 [2] = {work items, multi-chunk slots}. */
 size_t hvae_w1_max_work(int max_slots);
 size_t hvae_w1_max_partial_rows(int max_slots);
 int hvae_w1_plan(const int32_t* seg_start, const int32_t* n_unique, int max_slots, int32_t* chunk_base, int32_t* part_base,
-                 int32_t* work_slot, int32_t* n_work, void* stream);
+                 int32_t* work_slot, int32_t* multi_slot, int32_t* n_work, void* stream);
 /* dpre: d(pre-activation) rows of the batch, [rows, ld]; or, for data-parallel training, the all-gathered per-rank
  * buffers read in place: row u lives at dpre + (u / block_rows) * block_stride + (u % block_rows) * ld
  * (block_rows <= 0: one plain matrix).  partial: [hvae_w1_max_partial_rows(max_slots), ld] scratch. */
 int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_t* sorted_eid, const int32_t* ent_user,
                  const float* ent_val, int max_slots, const int32_t* chunk_base, const int32_t* part_base, const int32_t* work_slot,
-                 const int32_t* n_work, const float* dpre, int ld, int block_rows, int64_t block_stride, float* gs, float* partial,
-                 float* rownorm2, void* stream);
+                 const int32_t* multi_slot, const int32_t* n_work, const float* dpre, int ld, int block_rows, int64_t block_stride,
+                 float* gs, float* partial, float* rownorm2, void* stream);
 /* dense variant for the autograd-compatible path (atomics into a zeroed [N, ld] buffer). */
 int hvae_w1_grad_dense(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
                        const float* dpre, int ld, int h, float* dW1T, void* stream);

@@ -405,15 +405,20 @@ __global__ void __launch_bounds__(1024) w1_plan_kernel(const int32_t* __restrict
         if (threadIdx.x == 0) { carry_a += wsum_a[31]; carry_b += wsum_b[31]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { chunk_base[n] = carry_a; part_base[n] = carry_b; *n_work = carry_a; }
+    if (threadIdx.x == 0) { chunk_base[n] = carry_a; part_base[n] = carry_b; n_work[0] = carry_a; n_work[1] = 0; }
 }
 
+// work_slot[w] = slot of work item w; multi_slot[] = the slots that have several chunks (order irrelevant: every entry is
+// combined independently), *n_multi their count (reset by the plan kernel).
 __global__ void w1_expand_kernel(const int32_t* __restrict__ n_unique, const int32_t* __restrict__ chunk_base,
-                                 int32_t* __restrict__ work_slot, int max_slots) {
+                                 int32_t* __restrict__ work_slot, int max_slots, int32_t* __restrict__ multi_slot,
+                                 int32_t* __restrict__ n_multi) {
     pdl_prologue();
     const int sl = blockIdx.x * blockDim.x + threadIdx.x;
     if (sl >= max_slots || sl >= *n_unique) return;
-    for (int w = chunk_base[sl]; w < chunk_base[sl + 1]; ++w) work_slot[w] = sl;
+    const int w0 = chunk_base[sl], w1 = chunk_base[sl + 1];
+    for (int w = w0; w < w1; ++w) work_slot[w] = sl;
+    if (w1 - w0 > 1) multi_slot[atomicAdd(n_multi, 1)] = sl;
 }
 template <int NCHUNK>
 __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_work,
@@ -503,15 +508,15 @@ __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict_
     if (threadIdx.x == 0) rownorm2[slot] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
 }
 
-// Items with several chunks: gs[slot] = partial rows added in chunk order; row norm.  One CTA per slot, early exit otherwise.
-__global__ void __launch_bounds__(128) w1_combine_kernel(const int32_t* __restrict__ n_unique, const int32_t* __restrict__ chunk_base,
+// Items with several chunks: gs[slot] = partial rows added in chunk order; row norm.  One CTA per multi-chunk slot.
+__global__ void __launch_bounds__(128) w1_combine_kernel(const int32_t* __restrict__ n_multi, const int32_t* __restrict__ multi_slot,
+                                                         const int32_t* __restrict__ chunk_base,
                                                          const int32_t* __restrict__ part_base, const float* __restrict__ partial,
                                                          int ld4, float* __restrict__ gs, float* __restrict__ rownorm2) {
     pdl_prologue();
-    const int slot = blockIdx.x;
-    if (slot >= *n_unique) return;
+    if ((int)blockIdx.x >= *n_multi) return;
+    const int slot = multi_slot[blockIdx.x];
     const int nchunks = chunk_base[slot + 1] - chunk_base[slot];
-    if (nchunks <= 1) return;
     const float4* pr = reinterpret_cast<const float4*>(partial) + (size_t)part_base[slot] * ld4;
     float n2 = 0.f;
     for (int col4 = threadIdx.x; col4 < ld4; col4 += 128) {
@@ -645,23 +650,25 @@ int hvae_colsum(const float* X, int ld, int R, int C, float* out, float* workspa
 }
 
 // Work plan of hvae_w1_grad for the transposed batch (depends on the batch only).  chunk_base, part_base: int32 [max_slots+1];
-// work_slot: int32 [hvae_w1_max_work(max_slots)]; n_work: int32 [1].
+// work_slot: int32 [hvae_w1_max_work(max_slots)]; n_work: int32 [2] = {work items, multi-chunk slots};
+// multi_slot: int32 [hvae_w1_max_partial_rows(max_slots)].
 size_t hvae_w1_max_work(int max_slots) { return (size_t)max_slots + (size_t)max_slots / kW1Chunk + 1; }
 size_t hvae_w1_max_partial_rows(int max_slots) { return 2 * ((size_t)max_slots / kW1Chunk + 1); }
 
 int hvae_w1_plan(const int32_t* seg_start, const int32_t* n_unique, int max_slots, int32_t* chunk_base, int32_t* part_base,
-                 int32_t* work_slot, int32_t* n_work, void* stream) {
+                 int32_t* work_slot, int32_t* multi_slot, int32_t* n_work, void* stream) {
     if (max_slots == 0) return 0;
     launch_pdl(w1_plan_kernel, 1, 1024, 0, (cudaStream_t)stream, seg_start, n_unique, chunk_base, part_base, n_work);
-    launch_pdl(w1_expand_kernel, ceil_div(max_slots, 256), 256, 0, (cudaStream_t)stream, n_unique, chunk_base, work_slot, max_slots);
+    launch_pdl(w1_expand_kernel, ceil_div(max_slots, 256), 256, 0, (cudaStream_t)stream, n_unique, chunk_base, work_slot, max_slots, multi_slot,
+               n_work + 1);
     HVAE_LAUNCH_CHECK("w1_plan");
     return 0;
 }
 
 int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_t* sorted_eid, const int32_t* ent_user,
                  const float* ent_val, int max_slots, const int32_t* chunk_base, const int32_t* part_base, const int32_t* work_slot,
-                 const int32_t* n_work, const float* dpre, int ld, int block_rows, int64_t block_stride, float* gs, float* partial,
-                 float* rownorm2, void* stream) {
+                 const int32_t* multi_slot, const int32_t* n_work, const float* dpre, int ld, int block_rows, int64_t block_stride,
+                 float* gs, float* partial, float* rownorm2, void* stream) {
     HVAE_REQUIRE(ld % 4 == 0 && block_stride % 4 == 0, "w1_grad: ld=%d and the block stride must be multiples of 4", ld);
     if (block_rows <= 0) { block_rows = 0x7fffffff; block_stride = 0; }
     if (max_slots == 0) return 0;
@@ -673,7 +680,8 @@ int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_
     DISPATCH_NCHUNK(nch, (launch_pdl(w1_grad_kernel<NC>, max_work, 128, smem, (cudaStream_t)stream, 
                              seg_start, n_work, work_slot, chunk_base, part_base, sorted_eid, ent_user, ent_val, dpre, ld / 4, block_rows,
                              block_stride / 4, gs, partial, rownorm2)));
-    launch_pdl(w1_combine_kernel, max_slots, 128, 0, (cudaStream_t)stream, n_unique, chunk_base, part_base, partial, ld / 4, gs, rownorm2);
+    launch_pdl(w1_combine_kernel, (int)hvae_w1_max_partial_rows(max_slots), 128, 0, (cudaStream_t)stream, n_work + 1, multi_slot, chunk_base,
+               part_base, partial, ld / 4, gs, rownorm2);
     HVAE_LAUNCH_CHECK("w1_grad");
     return 0;
 }

@@ -536,11 +536,12 @@ class Engine:
         chunk_base = ws.get("w1_chunk_base", (cap + 1,), i32)
         part_base = ws.get("w1_part_base", (cap + 1,), i32)
         work_slot = ws.get("w1_work_slot", (int(lib.w1_max_work(cap)),), i32)
-        n_work = ws.get("w1_n_work", (1,), i32, zero=True)
-        lib.w1_plan(p(seg_start), p(n_unique), cap, p(chunk_base), p(part_base), p(work_slot), p(n_work), st)
+        multi_slot = ws.get("w1_multi_slot", (int(lib.w1_max_partial_rows(cap)),), i32)
+        n_work = ws.get("w1_n_work", (2,), i32, zero=True)
+        lib.w1_plan(p(seg_start), p(n_unique), cap, p(chunk_base), p(part_base), p(work_slot), p(multi_slot), p(n_work), st)
         return dict(cap=cap, seg_start=seg_start, n_unique=n_unique, eid_sorted=arr["eid_sorted"], ent_user=arr["ent_user"],
                     ent_val=ent_val, uniq=arr["uniq_item"], chunk_base=chunk_base, part_base=part_base, work_slot=work_slot,
-                    n_work=n_work)
+                    multi_slot=multi_slot, n_work=n_work)
 
     def w1_grad(self, tb, dpre_ptr, block_rows=0, block_stride=0):
         """d(W1^T) rows of the touched items (deterministic segment sums) and their squared norms.  dpre_ptr: device
@@ -552,7 +553,7 @@ class Engine:
         rn2 = ws.get("rownorm2", (tb["cap"],))
         part = ws.get("w1_partial", (int(lib.w1_max_partial_rows(tb["cap"])), ld1))
         lib.w1_grad(p(tb["seg_start"]), p(tb["n_unique"]), p(tb["eid_sorted"]), p(tb["ent_user"]), p(tb["ent_val"]), tb["cap"],
-                    p(tb["chunk_base"]), p(tb["part_base"]), p(tb["work_slot"]), p(tb["n_work"]), dpre_ptr, ld1, block_rows,
+                    p(tb["chunk_base"]), p(tb["part_base"]), p(tb["work_slot"]), p(tb["multi_slot"]), p(tb["n_work"]), dpre_ptr, ld1, block_rows,
                     block_stride, p(gs), p(part), p(rn2), self.stream)
         return gs, rn2
 
