@@ -28,6 +28,7 @@ struct TGemmParams {
     int M, N, K;
     int a_mn, b_mn;   // 1: operand is MN-major (m resp. n contiguous in memory)
     int stage_bytes, n_stages;
+    int ksplit;       // CTAs per output tile (cluster along z): each takes a contiguous range of k-blocks
     int direct;       // debug (HVAE_TF32_TRUNC=1, both operands K-major): skip the rounding pass, the MMA truncates
     float* C;
     int64_t ldc;
@@ -97,7 +98,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_c
     const int raw_a = TG_TILES, raw_b = TG_TILES + (P.a_mn ? TG_A_BYTES : 0);      // offsets of the raw areas in a stage
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
-    const int KB = (P.K + TG_BK - 1) / TG_BK;
+    const int KB_all = (P.K + TG_BK - 1) / TG_BK;
+    // split-K over a cluster of P.ksplit CTAs (these GEMMs are latency-bound per CTA: ~0.4 us per k-block, so the k loop is
+    // shared out); partial accumulators are reduced through the leader's shared memory (DSMEM) in rank order: deterministic
+    const int rank = P.ksplit > 1 ? (int)cluster_ctarank() : 0;
+    const int kb_lo = (int)((int64_t)rank * KB_all / P.ksplit), kb_hi = (int)((int64_t)(rank + 1) * KB_all / P.ksplit);
+    const int KB = kb_hi - kb_lo;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -121,17 +127,18 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_c
                 mbar_expect_tx(&bars->raw_full[s], TG_TILES);
                 uint8_t* a = smem + s * TG_STAGE;
                 uint8_t* b = a + TG_A_BYTES;
+                const int kg = (kb_lo + kb) * TG_BK;                                      // global k of this block
                 if (!P.a_mn) {
-                    tma_load_2d(a, &tmA, kb * TG_BK, m0, &bars->raw_full[s]);             // box {32 k, 128 m}, swizzled, final place
+                    tma_load_2d(a, &tmA, kg, m0, &bars->raw_full[s]);                     // box {32 k, 128 m}, swizzled, final place
                 } else {
                     for (int g = 0; g < TG_BM / 32; ++g)                                  // raw boxes {32 m, 32 k}
-                        tma_load_2d(a + raw_a + g * 4096, &tmA, m0 + g * 32, kb * TG_BK, &bars->raw_full[s]);
+                        tma_load_2d(a + raw_a + g * 4096, &tmA, m0 + g * 32, kg, &bars->raw_full[s]);
                 }
                 if (!P.b_mn) {
-                    tma_load_2d(b, &tmB, kb * TG_BK, n0, &bars->raw_full[s]);             // box {32 k, 64 n}
+                    tma_load_2d(b, &tmB, kg, n0, &bars->raw_full[s]);                     // box {32 k, 64 n}
                 } else {
                     for (int g = 0; g < TG_BN / 32; ++g)                                  // raw boxes {32 n, 32 k}
-                        tma_load_2d(a + raw_b + g * 4096, &tmB, n0 + g * 32, kb * TG_BK, &bars->raw_full[s]);
+                        tma_load_2d(a + raw_b + g * 4096, &tmB, n0 + g * 32, kg, &bars->raw_full[s]);
                 }
             }
         }
@@ -176,17 +183,48 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->full[s]);
         }
-        if (warp < 6) {                 // the epilogue needs only four warps (one per TMEM lane quarter)
-        const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
+    }
+    // ---- epilogue ---------------------------------------------------------------------------------------------------
+    const bool epi = warp >= 2 && warp < 6;          // four warps, one per TMEM lane quarter
+    const int q = warp & 3;
+    const int r_local = q * 32 + lane;
+    const int m = m0 + r_local;
+    if (epi) {
         mbar_wait(&bars->acc_full, 0);
         tc_fence_after();
+    }
+    if (P.ksplit > 1) {
+        cluster_sync_all();        // every CTA of the cluster has finished its k range: the leader's ring buffers are free
+        if (epi && rank > 0) {     // partial accumulator -> leader's shared memory, [rank-1][16-byte column chunk][row]
+            const uint32_t red = map_to_cta(smem_u32(smem), 0u) + (uint32_t)(rank - 1) * (TG_BN / 4) * TG_BM * 16;
+#pragma unroll 1
+            for (int c = 0; c < TG_BN / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    st_cluster_v4(red + (uint32_t)(((c * 8 + j / 4) * TG_BM + r_local) * 16), __float_as_uint(v[j]), __float_as_uint(v[j + 1]),
+                                  __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]));
+            }
+        }
+        cluster_sync_all();        // partials are visible in the leader
+    }
+    if (epi && rank == 0) {
         const bool vec = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+        const float4* red = reinterpret_cast<const float4*>(smem);
 #pragma unroll 1
         for (int c = 0; c < TG_BN / 32; ++c) {
             float v[32];
             tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + c * 32, v);
             tmem_ld_wait();
+            for (int pr = 0; pr < P.ksplit - 1; ++pr) {          // fixed rank order
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 t = red[(size_t)pr * (TG_BN / 4) * TG_BM + (c * 8 + j / 4) * TG_BM + r_local];
+                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                }
+            }
             if (m >= P.M) continue;
             const int nb = n0 + c * 32;
             float* crow = P.C + (int64_t)m * P.ldc + nb;
@@ -206,7 +244,6 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_c
                         if (nb + j + e < P.N) crow[j + e] = o[e];
                 }
             }
-        }
         }
     }
     tc_fence_before();
@@ -287,7 +324,36 @@ int hvae_gemm_tf32(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_
         attr_set = true;
     }
     dim3 grid(ceil_div(N, TG_BN), ceil_div(M, TG_BM));
-    launch_pdl(gemm_tf32_kernel, grid, TG_THREADS, kTGemmSmem, (cudaStream_t)stream, tmA, tmB, P);
+    const int tiles = grid.x * grid.y, KB = ceil_div(K, TG_BK);
+    static const bool no_split = getenv("HVAE_NO_SPLITK") != nullptr;
+    P.ksplit = 1;
+    if (!no_split) {
+        // split only while every CTA keeps >= 4 k-blocks (two cluster barriers + the DSMEM reduction cost ~1 us) and the whole
+        // grid stays within one wave (clusters of 4 strand some SMs: stay below 132 CTAs)
+        if (KB >= 16 && tiles * 4 <= 132) P.ksplit = 4;
+        else if (KB >= 8 && tiles * 2 <= 132) P.ksplit = 2;
+    }
+    grid.z = P.ksplit;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TG_THREADS);
+    cfg.dynamicSmemBytes = kTGemmSmem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (P.ksplit > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = P.ksplit;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    HVAE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel, tmA, tmB, P));
     HVAE_LAUNCH_CHECK("gemm_tf32");
     return 0;
 }
