@@ -184,6 +184,12 @@ int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_p
 int hvae_fill_noise(uint8_t* mask, int64_t n_mask, float keep_prob, float* eps, int64_t n_eps, uint64_t seed,
                     uint64_t offset, uint32_t stream_id, const hvae_step_state* state, void* stream);
 
+/* ---- data-parallel gradient exchange over NVLink / NVSwitch (new; the reference is single-process) ------------------- */
+/* One-shot all-gather by direct stores into every rank's symmetric receive buffer (NVSwitch multicast when mc_dst != NULL,
+ * else the `world` unicast peer mappings in peer_ptrs).  The caller brackets it with symmetric-memory barriers. */
+int hvae_nvl_push(const float* src, int64_t n, float* mc_dst, const uint64_t* peer_ptrs, int world, int64_t dst_off,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,6 +159,28 @@ __global__ void noise_normal_kernel(float* __restrict__ eps, int64_t n, uint64_t
     }
 }
 
+// One-shot all-gather over NVLink / NVSwitch: every rank stores its block straight into the other ranks' receive
+// buffers -- through the NVSwitch multicast address when there is one (one store, the switch replicates it: multimem.st),
+// else through the peers' unicast mappings.  Ordering across ranks comes from the symmetric-memory barrier the caller
+// issues before (receive buffers free) and after (stores visible) this kernel.
+__global__ void __launch_bounds__(256) nvl_push_kernel(const float4* __restrict__ src, int64_t n4, float* mc_dst,
+                                                       const uint64_t* __restrict__ peer_ptrs, int world, int64_t dst_off) {
+    pdl_prologue();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = src[i];
+    if (mc_dst) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + dst_off + 4 * i), "f"(v.x), "f"(v.y),
+                     "f"(v.z), "f"(v.w)
+                     : "memory");
+    } else {
+        for (int r = 0; r < world; ++r) {
+            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(peer_ptrs[r]) + dst_off) + i;
+            asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+    }
+}
+
 }  // namespace hvae
 
 using namespace hvae;
@@ -206,6 +228,17 @@ int hvae_fill_noise(uint8_t* mask, int64_t n_mask, float keep_prob, float* eps, 
         launch_pdl(noise_normal_kernel, (unsigned)((n_eps / 4 + 256) / 256), 256, 0, (cudaStream_t)stream, eps, n_eps, seed, offset,
                                                                                                     stream_id + 0x80000000u, state);
     HVAE_LAUNCH_CHECK("fill_noise");
+    return 0;
+}
+
+// src: n floats (multiple of 4, 16-byte aligned) of this rank; destination = offset dst_off (floats) inside every rank's
+// symmetric receive buffer: mc_dst = its multicast address (or NULL), peer_ptrs = device array of the `world` unicast addresses.
+int hvae_nvl_push(const float* src, int64_t n, float* mc_dst, const uint64_t* peer_ptrs, int world, int64_t dst_off, void* stream) {
+    HVAE_REQUIRE(n % 4 == 0 && dst_off % 4 == 0, "nvl_push: sizes and offsets must be multiples of 4 floats");
+    if (n == 0) return 0;
+    launch_pdl(nvl_push_kernel, (unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream, (const float4*)src, n / 4, mc_dst, peer_ptrs,
+               world, dst_off);
+    HVAE_LAUNCH_CHECK("nvl_push");
     return 0;
 }
 

@@ -21,6 +21,8 @@ behind `Engine` need a GPU.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -94,6 +96,10 @@ class DataParallel:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        # gradient exchange: "nvl" = our one-shot all-gather by direct (multicast) stores into symmetric memory,
+        # "nccl" = NCCL all-gather.  "auto" tries nvl and falls back to nccl if symmetric memory cannot be set up.
+        self.exchange_mode = os.environ.get("HVAE_DP_EXCHANGE", "auto")
+        self._sym = None
 
     # -- batch splitting -------------------------------------------------------------------------------------
     def local_rows(self, global_rows):
@@ -155,7 +161,49 @@ class DataParallel:
         cap = batch.nnz_cap_global if getattr(batch, "nnz_cap_global", None) else batch.nnz_cap * self.world
         return Batch(batch.csr, rows_all, rows_all.shape[0], cap)
 
+    def _symmetric(self, eng, n_floats):
+        """Symmetric receive buffer [world * stride] + peer / multicast addresses (torch symmetric memory: CUDA VMM)."""
+        if self._sym is not None and self._sym["n"] >= n_floats:
+            return self._sym
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(n_floats, dtype=torch.float32, device=eng.dev)
+        hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+        mc = int(hdl.multicast_ptr or 0)                 # 0 when the fabric has no multicast (NVLS) support
+        self._sym = dict(n=n_floats, buf=t, hdl=hdl, mc=mc, peers=int(hdl.buffer_ptrs_dev))
+        eng.ws.generation += 1          # captured graphs must not keep pointers into an older buffer
+        return self._sym
+
     def exchange_grads(self, eng, batch, dpre0):
+        if self.exchange_mode in ("auto", "nvl"):
+            try:
+                return self._exchange_grads_nvl(eng, batch, dpre0)
+            except Exception:
+                if self.exchange_mode == "nvl":
+                    raise
+                self.exchange_mode = "nccl"
+        return self._exchange_grads_nccl(eng, batch, dpre0)
+
+    def _exchange_grads_nvl(self, eng, batch, dpre0):
+        """Our own all-gather: every rank stores [dense gradients | dH1 rows] directly into all ranks' symmetric receive
+        buffers (one NVSwitch-multicast store stream), bracketed by two symmetric-memory barriers; then the same fixed-order
+        sum of the dense gradients and in-place consumption of the dH1 blocks as the NCCL path."""
+        from ._cabi import p
+        n_dense = eng.gd.numel()
+        bm, B, ld = self.b_max(eng.b_global), batch.B, dpre0.shape[1]
+        stride = n_dense + bm * ld
+        sym = self._symmetric(eng, self.world * stride)
+        hdl, recv = sym["hdl"], sym["buf"]
+        st = eng.stream
+        hdl.barrier(channel=0)                       # every rank has consumed the previous step's blocks
+        off = self.rank * stride
+        eng.lib.nvl_push(p(eng.gd), n_dense, sym["mc"] or None, sym["peers"], self.world, off, st)
+        eng.lib.nvl_push(p(dpre0), B * ld, sym["mc"] or None, sym["peers"], self.world, off + n_dense, st)
+        hdl.barrier(channel=1)                       # all stores have landed everywhere
+        cs = eng.ws.get("dp_colsum_ws", (n_dense + 64,))
+        eng.lib.colsum(p(recv), stride, self.world, n_dense, p(eng.gd), p(cs), st)
+        return recv.data_ptr() + 4 * n_dense, bm, stride
+
+    def _exchange_grads_nccl(self, eng, batch, dpre0):
         """ONE all-gather per step: every rank sends [its dense gradients | its dH1 rows]; the dense gradients are then
         summed over ranks in a fixed order by our column-sum kernel (identical bits on every rank) and the layer-1
         weight-gradient kernel reads the gathered dH1 blocks in place.  -> (pointer to rank 0's dH1 block, rows per block,
