@@ -7,6 +7,8 @@
 //  (3) hvae_w1_grad : backward of (1): per touched item, sum_b x_bi * dH_b, written to a compact
 //      [n_unique, ld] gradient (deterministic, no atomics) together with its squared norm.
 // HBM-bound; one warp owns one row, 128-bit loads, shuffle reductions.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hvae {
@@ -159,6 +161,18 @@ __global__ void __launch_bounds__(512) gather_ln_fwd_block_kernel(
     const bool on = t < ld4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int64_t j = s;
+    for (; j + 8 <= e; j += 8) {      // eight rows in flight per thread
+        int id[8]; float xv[8]; float4 w[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { id[q] = indices[j + q]; xv[q] = values ? values[j + q] : 1.0f; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) w[q] = on ? __ldg(W1T + (size_t)id[q] * ld4 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            acc.x = fmaf(xv[q], w[q].x, acc.x); acc.y = fmaf(xv[q], w[q].y, acc.y);
+            acc.z = fmaf(xv[q], w[q].z, acc.z); acc.w = fmaf(xv[q], w[q].w, acc.w);
+        }
+    }
     for (; j + 4 <= e; j += 4) {      // four rows in flight per thread
         int id[4]; float xv[4]; float4 w[4];
 #pragma unroll
@@ -577,7 +591,7 @@ int hvae_gather_ln_fwd(const int64_t* indptr, const int32_t* indices, const floa
                        void* stream) {
     HVAE_REQUIRE(ld % 4 == 0 && ld >= h, "gather_ln_fwd: ld=%d must be a multiple of 4 and >= h=%d", ld, h);
     if (B == 0) return 0;
-    if (B < 2048 && ld / 4 <= 512) {   // small batch: one CTA per user (more loads in flight)
+    if (ld / 4 <= 512 && getenv("HVAE_GATHER_WARP") == nullptr) {   // one CTA per user (more loads in flight than a warp per user)
         launch_pdl(gather_ln_fwd_block_kernel, B, round_up(ld / 4, 32), (size_t)ld * sizeof(float), (cudaStream_t)stream, 
             indptr, indices, values, rows, B, reinterpret_cast<const float4*>(W1T), ld / 4, h, bias, gamma, beta, mask, keep_scale, pre,
             mean, rstd, act);
