@@ -128,9 +128,12 @@ int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const fl
 int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
                      const float* O, int ldo, int n_parts, const float* oscale, const void* E, int lde, int d, int is_bf16,
                      const float* inv_bg, float* dU, int lddu, void* stream);
+/* Seen-item masking (in place) + top-K of materialised scores under the order (score desc, index desc).  Rows are cut into
+ * hvae_mask_topk_chunks(n_rows, N) column chunks; cand_val / cand_idx: scratch [n_rows, chunks * K] (NULL if chunks == 1). */
+size_t hvae_mask_topk_chunks(int n_rows, int N);
 int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, const int64_t* indptr,
-                   const int32_t* indices, const int32_t* rows, int exclude_seen, int K, float* out_val,
-                   int32_t* out_idx, void* stream);
+                   const int32_t* indices, const int32_t* rows, int exclude_seen, int K, float* cand_val, int32_t* cand_idx,
+                   float* out_val, int32_t* out_idx, void* stream);
 int hvae_topk_merge(const float* cval, const int32_t* cidx, int n_rows, int GK, int K, float* out_val, int32_t* out_idx,
                     void* stream);
 /* Negative-sampling protocol (evaluate.py:149-185): scores of C candidates per row (candidate 0 = test item) and the

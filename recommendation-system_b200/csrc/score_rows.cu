@@ -230,56 +230,114 @@ __device__ __forceinline__ void topk_insert(float* sv, int* si, int K, float cv,
     __syncwarp();
 }
 
-constexpr int kTopkWarps = 4;
-constexpr int kMaxK = 128;
-
-__global__ void __launch_bounds__(kTopkWarps * 32) mask_topk_kernel(float* __restrict__ S, int64_t lds, int n_rows, int N,
-                                                                    int item_offset, const int64_t* __restrict__ indptr,
-                                                                    const int32_t* __restrict__ indices,
-                                                                    const int32_t* __restrict__ rows, int exclude_seen, int K,
-                                                                    float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
-    pdl_prologue();
-    __shared__ float sv_all[kTopkWarps][kMaxK];
-    __shared__ int si_all[kTopkWarps][kMaxK];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * kTopkWarps + warp;
-    if (r >= n_rows) return;
-    float* sv = sv_all[warp];
-    int* si = si_all[warp];
-    float* row = S + (size_t)r * lds;
-    for (int e = lane; e < K; e += 32) { sv[e] = -INFINITY; si[e] = -1; }
-    if (exclude_seen) {
-        const int u = rows ? rows[r] : r;
-        for (int64_t j = indptr[u] + lane; j < indptr[u + 1]; j += 32) {
-            const int c = indices[j] - item_offset;
-            if (c >= 0 && c < N) row[c] = -INFINITY;
+// Warp-level running top-K under the total order (score desc, index desc).  K <= 32: the list lives in registers, one
+// entry per lane, sorted best-first -- an insertion is a ballot, a popcount and two shuffles.  K <= 128: sorted list in
+// shared memory (topk_insert).  offer() is warp-uniform: every lane offers one (value, id); id < 0 = nothing to offer.
+struct WarpTopK {
+    float lv; int li;            // register list (K <= 32): lane l holds the l-th best
+    float* sv; int* si;          // shared-memory list (K > 32)
+    float thr_v; int thr_i;
+    int K, lane;
+    bool in_regs;
+    __device__ __forceinline__ void init(int K_, int lane_, float* sv_, int* si_) {
+        K = K_; lane = lane_; sv = sv_; si = si_; in_regs = K_ <= 32;
+        lv = -INFINITY; li = -1; thr_v = -INFINITY; thr_i = -1;
+        if (!in_regs) { for (int e = lane; e < K; e += 32) { sv[e] = -INFINITY; si[e] = -1; } __syncwarp(); }
+    }
+    __device__ __forceinline__ void insert(float cv, int ci) {      // warp-uniform (cv, ci)
+        if (in_regs) {
+            const int pos = __popc(__ballot_sync(0xffffffffu, better(lv, li, cv, ci)));    // entries ahead of the candidate
+            if (pos >= K) return;
+            const float uv = __shfl_up_sync(0xffffffffu, lv, 1);
+            const int ui = __shfl_up_sync(0xffffffffu, li, 1);
+            if (lane == pos) { lv = cv; li = ci; }
+            else if (lane > pos) { lv = uv; li = ui; }
+            if (lane >= K) { lv = -INFINITY; li = -1; }
+            thr_v = __shfl_sync(0xffffffffu, lv, K - 1);
+            thr_i = __shfl_sync(0xffffffffu, li, K - 1);
+        } else {
+            topk_insert(sv, si, K, cv, ci, lane);
+            thr_v = sv[K - 1];
+            thr_i = si[K - 1];
         }
     }
-    __syncwarp();
-    float thr_v = -INFINITY;
-    int thr_i = -1;
-    for (int base = 0; base < N; base += 32) {
-        const int c = base + lane;
-        const float v = c < N ? row[c] : -INFINITY;
-        const int gi = c < N ? item_offset + c : -2;
-        unsigned bal = __ballot_sync(0xffffffffu, better(v, gi, thr_v, thr_i));
+    __device__ __forceinline__ void offer(float v, int gi) {
+        unsigned bal = __ballot_sync(0xffffffffu, gi >= 0 && better(v, gi, thr_v, thr_i));
         while (bal) {
             const int src = __ffs(bal) - 1;
             bal &= bal - 1;
             const float cv = __shfl_sync(0xffffffffu, v, src);
             const int ci = __shfl_sync(0xffffffffu, gi, src);
-            if (better(cv, ci, thr_v, thr_i)) {
-                topk_insert(sv, si, K, cv, ci, lane);
-                thr_v = sv[K - 1];
-                thr_i = si[K - 1];
-            }
+            if (better(cv, ci, thr_v, thr_i)) insert(cv, ci);
+        }
+    }
+    __device__ __forceinline__ void store(float* ov, int32_t* oi) {
+        if (in_regs) { if (lane < K) { ov[lane] = lv; oi[lane] = li; } }
+        else { __syncwarp(); for (int e = lane; e < K; e += 32) { ov[e] = sv[e]; oi[e] = si[e]; } }
+    }
+};
+
+constexpr int kTopkWarps = 4;
+constexpr int kMaxK = 128;
+
+// One warp per (score row, column chunk): seen-item masking + top-K of the chunk under the total order
+// (score desc, index desc).  Large catalogues are cut into chunks so that every SM has work (a row of 1M scores is 4 MB:
+// one warp per row would leave the machine idle); the per-chunk lists are then reduced by topk_merge_kernel.
+// Scores are streamed with 16-byte loads when the row stride allows it.
+__global__ void __launch_bounds__(kTopkWarps * 32) mask_topk_kernel(float* __restrict__ S, int64_t lds, int n_rows, int N,
+                                                                    int item_offset, const int64_t* __restrict__ indptr,
+                                                                    const int32_t* __restrict__ indices,
+                                                                    const int32_t* __restrict__ rows, int exclude_seen, int K,
+                                                                    int n_chunks, int chunk_len, float* __restrict__ out_val,
+                                                                    int32_t* __restrict__ out_idx) {
+    pdl_prologue();
+    __shared__ float sv_all[kTopkWarps][kMaxK];
+    __shared__ int si_all[kTopkWarps][kMaxK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t unit = (int64_t)blockIdx.x * kTopkWarps + warp;
+    if (unit >= (int64_t)n_rows * n_chunks) return;
+    const int r = (int)(unit / n_chunks), ch = (int)(unit - (int64_t)r * n_chunks);
+    const int c0 = ch * chunk_len, c1 = min(N, c0 + chunk_len);
+    float* row = S + (size_t)r * lds;
+    if (exclude_seen) {
+        const int u = rows ? rows[r] : r;
+        for (int64_t j = indptr[u] + lane; j < indptr[u + 1]; j += 32) {
+            const int c = indices[j] - item_offset;
+            if (c >= c0 && c < c1) row[c] = -INFINITY;
         }
     }
     __syncwarp();
-    for (int e = lane; e < K; e += 32) {
-        out_val[(size_t)r * K + e] = sv[e];
-        out_idx[(size_t)r * K + e] = si[e];
+    WarpTopK top;
+    top.init(K, lane, sv_all[warp], si_all[warp]);
+    const bool vec = (lds % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (c0 % 4 == 0);
+    if (vec) {
+        const int c1v = c0 + ((c1 - c0) / 4) * 4;
+        const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        // three 512-byte row segments in flight per warp; a segment with no candidate (the common case once the threshold
+        // has risen) costs four compares and one vote
+        auto fetch = [&](int base) { const int c = base + lane * 4; return (base < c1v && c < c1v) ? *reinterpret_cast<const float4*>(row + c) : ninf; };
+        float4 n0 = fetch(c0), n1 = fetch(c0 + 128), n2 = fetch(c0 + 256);
+        for (int base = c0; base < c1v; base += 128) {
+            const int c = base + lane * 4;
+            const float4 v = n0;
+            n0 = n1; n1 = n2; n2 = fetch(base + 384);
+            const int g = c < c1v ? item_offset + c : -8;
+            const bool any = g >= 0 && (better(v.x, g, top.thr_v, top.thr_i) || better(v.y, g + 1, top.thr_v, top.thr_i) ||
+                                        better(v.z, g + 2, top.thr_v, top.thr_i) || better(v.w, g + 3, top.thr_v, top.thr_i));
+            if (!__any_sync(0xffffffffu, any)) continue;
+            top.offer(v.x, g);
+            top.offer(v.y, g + 1);
+            top.offer(v.z, g + 2);
+            top.offer(v.w, g + 3);
+        }
+        { const int c = c1v + lane; top.offer(c < c1 ? row[c] : -INFINITY, c < c1 ? item_offset + c : -1); }    // <= 3 tail columns
+    } else {
+        for (int base = c0; base < c1; base += 32) {
+            const int c = base + lane;
+            top.offer(c < c1 ? row[c] : -INFINITY, c < c1 ? item_offset + c : -1);
+        }
     }
+    top.store(out_val + ((size_t)r * n_chunks + ch) * K, out_idx + ((size_t)r * n_chunks + ch) * K);
 }
 
 // Merge G sorted candidate lists per row (item-sharded evaluation): cand [n_rows, G*K] -> top K.
@@ -292,20 +350,13 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_merge_kernel(const float
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * kTopkWarps + warp;
     if (r >= n_rows) return;
-    float* sv = sv_all[warp];
-    int* si = si_all[warp];
-    for (int e = lane; e < K; e += 32) { sv[e] = -INFINITY; si[e] = -1; }
-    __syncwarp();
-    for (int j = 0; j < GK; ++j) {
-        const float cv = cval[(size_t)r * GK + j];
-        const int ci = cidx[(size_t)r * GK + j];
-        if (ci >= 0 && better(cv, ci, sv[K - 1], si[K - 1])) topk_insert(sv, si, K, cv, ci, lane);
+    WarpTopK top;
+    top.init(K, lane, sv_all[warp], si_all[warp]);
+    for (int base = 0; base < GK; base += 32) {
+        const int j = base + lane;
+        top.offer(j < GK ? cval[(size_t)r * GK + j] : -INFINITY, j < GK ? cidx[(size_t)r * GK + j] : -1);
     }
-    __syncwarp();
-    for (int e = lane; e < K; e += 32) {
-        out_val[(size_t)r * K + e] = sv[e];
-        out_idx[(size_t)r * K + e] = si[e];
-    }
+    top.store(out_val + (size_t)r * K, out_idx + (size_t)r * K);
 }
 
 // hit mask: bit p of mask[r] (4 x u32 per row) is set iff topk[r][p] is one of the row's relevant items.
@@ -445,13 +496,41 @@ int hvae_candidate_rank(const void* U, int ldu, const void* E, int lde, int d, i
     return 0;
 }
 
+// Column chunks per row: enough (row, chunk) warps to fill the machine (~8k), chunks of at least 4096 scores, multiples of 128.
+static void topk_chunks(int n_rows, int N, int* n_chunks, int* chunk_len) {
+    int want = max(1, 8192 / max(1, n_rows));
+    int len = max(4096, ceil_div(N, want));
+    len = round_up(len, 128);
+    *chunk_len = len;
+    *n_chunks = max(1, ceil_div(N, len));
+}
+
+size_t hvae_mask_topk_chunks(int n_rows, int N) {
+    int nc, len;
+    topk_chunks(n_rows, N, &nc, &len);
+    return (size_t)nc;
+}
+
+// scratch cand_val / cand_idx: [n_rows, hvae_mask_topk_chunks(n_rows, N) * K] (may be NULL when that is 1)
 int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, const int64_t* indptr, const int32_t* indices,
-                   const int32_t* rows, int exclude_seen, int K, float* out_val, int32_t* out_idx, void* stream) {
+                   const int32_t* rows, int exclude_seen, int K, float* cand_val, int32_t* cand_idx, float* out_val, int32_t* out_idx,
+                   void* stream) {
     HVAE_REQUIRE(K >= 1 && K <= kMaxK, "mask_topk: K=%d outside [1,%d]", K, kMaxK);
     if (n_rows == 0) return 0;
-    launch_pdl(mask_topk_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, 
-        S, lds, n_rows, N, item_offset, indptr, indices, rows, exclude_seen, K, out_val, out_idx);
+    int nc, len;
+    topk_chunks(n_rows, N, &nc, &len);
+    HVAE_REQUIRE(nc == 1 || (cand_val && cand_idx), "mask_topk: %d column chunks need candidate scratch", nc);
+    const int64_t units = (int64_t)n_rows * nc;
+    float* cv = nc == 1 ? out_val : cand_val;
+    int32_t* ci = nc == 1 ? out_idx : cand_idx;
+    launch_pdl(mask_topk_kernel, (unsigned)((units + kTopkWarps - 1) / kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, S, lds, n_rows, N,
+               item_offset, indptr, indices, rows, exclude_seen, K, nc, len, cv, ci);
     HVAE_LAUNCH_CHECK("mask_topk");
+    if (nc > 1) {
+        launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, (const float*)cand_val,
+                   (const int32_t*)cand_idx, n_rows, nc * K, K, out_val, out_idx);
+        HVAE_LAUNCH_CHECK("mask_topk merge");
+    }
     return 0;
 }
 

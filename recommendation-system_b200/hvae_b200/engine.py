@@ -626,6 +626,9 @@ class Engine:
             nb = min(bc, B - r0)
             self.gemm(nb, n_it, d, u.data_ptr() + 4 * r0 * ldd, ldd, 1, self.E.data_ptr() + 4 * item_lo * d, 1, d, p(S), n_it)
             rows_ptr = rows.data_ptr() + 4 * r0
+            nc = int(lib.mask_topk_chunks(nb, n_it))
+            cv = ws.get("topk_cand_v", (nb, nc * K))
+            ci = ws.get("topk_cand_i", (nb, nc * K), torch.int32)
             lib.mask_topk(p(S), n_it, nb, n_it, item_lo, p(csr.indptr), p(csr.indices), rows_ptr, 1 if exclude_seen else 0, K,
-                          out_val.data_ptr() + 4 * r0 * K, out_idx.data_ptr() + 4 * r0 * K, st)
+                          p(cv), p(ci), out_val.data_ptr() + 4 * r0 * K, out_idx.data_ptr() + 4 * r0 * K, st)
         return out_val, out_idx

@@ -217,7 +217,11 @@ class HybridVAE(nn.Module):
             val = torch.empty(B, top_k, dtype=torch.float32, device=s2.device)
             idx = torch.empty(B, top_k, dtype=torch.int32, device=s2.device)
             zero_ptr = torch.zeros(B + 1, dtype=torch.int64, device=s2.device)
-            eng.lib.mask_topk(p(s2), s2.shape[1], B, s2.shape[1], 0, p(zero_ptr), None, None, 0, top_k, p(val), p(idx), eng.stream)
+            nc = int(eng.lib.mask_topk_chunks(B, s2.shape[1]))
+            cv = torch.empty(B, nc * top_k, dtype=torch.float32, device=s2.device)
+            ci = torch.empty(B, nc * top_k, dtype=torch.int32, device=s2.device)
+            eng.lib.mask_topk(p(s2), s2.shape[1], B, s2.shape[1], 0, p(zero_ptr), None, None, 0, top_k, p(cv), p(ci), p(val), p(idx),
+                              eng.stream)
         return idx.long(), val
 
 

@@ -83,7 +83,7 @@ def test_topk_order_and_masking(dev):
     lib = _cabi.lib()
     st = torch.cuda.current_stream().cuda_stream
     rng = np.random.default_rng(0)
-    for (R, N, K) in [(7, 1000, 20), (3, 37, 37), (5, 4099, 128), (4, 50, 100 if False else 50)]:
+    for (R, N, K) in [(7, 1000, 20), (3, 37, 37), (5, 4099, 128), (4, 50, 50), (3, 70001, 20), (2, 40000, 100)]:
         S = rng.standard_normal((R, N)).astype(np.float32)
         S[:, ::7] = np.round(S[:, ::7], 1)           # plenty of exact ties
         seen_ptr, seen_idx = [0], []
@@ -96,7 +96,11 @@ def test_topk_order_and_masking(dev):
         ix = torch.tensor(seen_idx, dtype=torch.int32, device=dev)
         val = torch.empty(R, K, device=dev)
         idx = torch.empty(R, K, dtype=torch.int32, device=dev)
-        lib.mask_topk(Sd.data_ptr(), N, R, N, 0, ip.data_ptr(), ix.data_ptr(), None, 1, K, val.data_ptr(), idx.data_ptr(), st)
+        nc = int(lib.mask_topk_chunks(R, N))
+        cv = torch.empty(R, nc * K, device=dev)
+        ci = torch.empty(R, nc * K, dtype=torch.int32, device=dev)
+        lib.mask_topk(Sd.data_ptr(), N, R, N, 0, ip.data_ptr(), ix.data_ptr(), None, 1, K, cv.data_ptr(), ci.data_ptr(), val.data_ptr(),
+                      idx.data_ptr(), st)
         for r in range(R):
             s = S[r].copy()
             s[seen_idx[seen_ptr[r]:seen_ptr[r + 1]]] = -np.inf
