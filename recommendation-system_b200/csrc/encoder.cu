@@ -160,36 +160,24 @@ __global__ void __launch_bounds__(512) gather_ln_fwd_block_kernel(
     const int64_t s = indptr[u], e = indptr[u + 1];
     const bool on = t < ld4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int64_t j = s;
-    for (; j + 8 <= e; j += 8) {      // eight rows in flight per thread
+    // eight rows in flight per thread; the ragged tail is a predicated batch (not a serial loop: every dependent
+    // indices -> row round trip costs a full memory latency), entries still accumulated in CSR order
+    for (int64_t j = s; j < e; j += 8) {
+        const int n = (int)min((int64_t)8, e - j);
         int id[8]; float xv[8]; float4 w[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { id[q] = indices[j + q]; xv[q] = values ? values[j + q] : 1.0f; }
+        for (int q = 0; q < 8; ++q) {
+            id[q] = q < n ? indices[j + q] : 0;
+            xv[q] = (values && q < n) ? values[j + q] : 1.0f;
+        }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) w[q] = on ? __ldg(W1T + (size_t)id[q] * ld4 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 8; ++q) w[q] = (on && q < n) ? __ldg(W1T + (size_t)id[q] * ld4 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            acc.x = fmaf(xv[q], w[q].x, acc.x); acc.y = fmaf(xv[q], w[q].y, acc.y);
-            acc.z = fmaf(xv[q], w[q].z, acc.z); acc.w = fmaf(xv[q], w[q].w, acc.w);
-        }
-    }
-    for (; j + 4 <= e; j += 4) {      // four rows in flight per thread
-        int id[4]; float xv[4]; float4 w[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { id[q] = indices[j + q]; xv[q] = values ? values[j + q] : 1.0f; }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) w[q] = on ? __ldg(W1T + (size_t)id[q] * ld4 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            acc.x = fmaf(xv[q], w[q].x, acc.x); acc.y = fmaf(xv[q], w[q].y, acc.y);
-            acc.z = fmaf(xv[q], w[q].z, acc.z); acc.w = fmaf(xv[q], w[q].w, acc.w);
-        }
-    }
-    for (; j < e; ++j) {
-        const float xv = values ? values[j] : 1.0f;
-        if (on) {
-            const float4 w = __ldg(W1T + (size_t)indices[j] * ld4 + t);
-            acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y); acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
+            if (q < n) {
+                acc.x = fmaf(xv[q], w[q].x, acc.x); acc.y = fmaf(xv[q], w[q].y, acc.y);
+                acc.z = fmaf(xv[q], w[q].z, acc.z); acc.w = fmaf(xv[q], w[q].w, acc.w);
+            }
         }
     }
     const int col = t * 4;

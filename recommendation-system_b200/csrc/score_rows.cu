@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) candidate_rank_kernel(const T* __restrict
 __device__ __forceinline__ bool better(float v, int i, float tv, int ti) { return v > tv || (v == tv && i > ti); }
 
 // One warp per score row.  The list (sv, si) lives in shared memory sorted best-first.
-__device__ __forceinline__ void topk_insert(float* sv, int* si, int K, float cv, int ci, int lane) {
+__device__ __noinline__ void topk_insert(float* sv, int* si, int K, float cv, int ci, int lane) {
     int cnt = 0;
     for (int e = lane; e < K; e += 32) cnt += better(sv[e], si[e], cv, ci) ? 1 : 0;
 #pragma unroll
@@ -233,18 +233,24 @@ __device__ __forceinline__ void topk_insert(float* sv, int* si, int K, float cv,
 // Warp-level running top-K under the total order (score desc, index desc).  K <= 32: the list lives in registers, one
 // entry per lane, sorted best-first -- an insertion is a ballot, a popcount and two shuffles.  K <= 128: sorted list in
 // shared memory (topk_insert).  offer() is warp-uniform: every lane offers one (value, id); id < 0 = nothing to offer.
+// (thr_v, thr_i) is the admission threshold: only elements better than it are looked at.  It never decreases; besides the
+// list's own K-th entry it can be raised from outside (raise()) by any pair known to have K elements at or above it.
 struct WarpTopK {
     float lv; int li;            // register list (K <= 32): lane l holds the l-th best
     float* sv; int* si;          // shared-memory list (K > 32)
     float thr_v; int thr_i;
     int K, lane;
-    bool in_regs;
+    bool in_regs, improved;
     __device__ __forceinline__ void init(int K_, int lane_, float* sv_, int* si_) {
-        K = K_; lane = lane_; sv = sv_; si = si_; in_regs = K_ <= 32;
+        K = K_; lane = lane_; sv = sv_; si = si_; in_regs = K_ <= 32; improved = false;
         lv = -INFINITY; li = -1; thr_v = -INFINITY; thr_i = -1;
         if (!in_regs) { for (int e = lane; e < K; e += 32) { sv[e] = -INFINITY; si[e] = -1; } __syncwarp(); }
     }
+    __device__ __forceinline__ void raise(float v, int i) {
+        if (better(v, i, thr_v, thr_i)) { thr_v = v; thr_i = i; }
+    }
     __device__ __forceinline__ void insert(float cv, int ci) {      // warp-uniform (cv, ci)
+        float kv; int ki;
         if (in_regs) {
             const int pos = __popc(__ballot_sync(0xffffffffu, better(lv, li, cv, ci)));    // entries ahead of the candidate
             if (pos >= K) return;
@@ -253,13 +259,14 @@ struct WarpTopK {
             if (lane == pos) { lv = cv; li = ci; }
             else if (lane > pos) { lv = uv; li = ui; }
             if (lane >= K) { lv = -INFINITY; li = -1; }
-            thr_v = __shfl_sync(0xffffffffu, lv, K - 1);
-            thr_i = __shfl_sync(0xffffffffu, li, K - 1);
+            kv = __shfl_sync(0xffffffffu, lv, K - 1);
+            ki = __shfl_sync(0xffffffffu, li, K - 1);
         } else {
             topk_insert(sv, si, K, cv, ci, lane);
-            thr_v = sv[K - 1];
-            thr_i = si[K - 1];
+            kv = sv[K - 1];
+            ki = si[K - 1];
         }
+        if (better(kv, ki, thr_v, thr_i)) { thr_v = kv; thr_i = ki; improved = true; }
     }
     __device__ __forceinline__ void offer(float v, int gi) {
         unsigned bal = __ballot_sync(0xffffffffu, gi >= 0 && better(v, gi, thr_v, thr_i));
@@ -279,11 +286,19 @@ struct WarpTopK {
 
 constexpr int kTopkWarps = 4;
 constexpr int kMaxK = 128;
+constexpr int kTopkSeg = 8;          // 512-byte row segments per trip of the scan (and as many again in flight)
 
 // One warp per (score row, column chunk): seen-item masking + top-K of the chunk under the total order
-// (score desc, index desc).  Large catalogues are cut into chunks so that every SM has work (a row of 1M scores is 4 MB:
-// one warp per row would leave the machine idle); the per-chunk lists are then reduced by topk_merge_kernel.
-// Scores are streamed with 16-byte loads when the row stride allows it.
+// (score desc, index desc); the per-chunk lists of a row are then reduced by topk_merge_kernel.
+// What the scan costs is set by how often a trip (4 KB = 1024 scores) holds a candidate, i.e. a score at or above the
+// list's current K-th best: after n scores that happens with probability ~min(1, 1024 K / n), so the threshold only does
+// its job once a warp has seen a few hundred K scores.  Hence LONG chunks (>= 64k scores when the launch has enough rows,
+// see topk_chunks) on FEW warps per SM, and memory latency is covered by depth instead of occupancy: 16-byte loads, eight
+// segments in registers and the next eight in flight per warp (~100 registers).  Fast path per trip: the lane's maximum of
+// its 32 scores against the threshold and one vote.  Candidates are taken straight from the registers: a ballot per
+// segment finds the lanes, four shuffles bring the lane's scores to the whole warp, insertion is warp-uniform.
+// The first trip doubles as a probe: the K-th largest of the 32 per-lane maxima has K scores at or above it, so it is a
+// valid threshold before the first insertion (about rank 40 of the trip's 1024 scores: most of the warm-up is skipped).
 __global__ void __launch_bounds__(kTopkWarps * 32) mask_topk_kernel(float* __restrict__ S, int64_t lds, int n_rows, int N,
                                                                     int item_offset, const int64_t* __restrict__ indptr,
                                                                     const int32_t* __restrict__ indices,
@@ -309,34 +324,66 @@ __global__ void __launch_bounds__(kTopkWarps * 32) mask_topk_kernel(float* __res
     __syncwarp();
     WarpTopK top;
     top.init(K, lane, sv_all[warp], si_all[warp]);
-    const bool vec = (lds % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (c0 % 4 == 0);
-    if (vec) {
-        const int c1v = c0 + ((c1 - c0) / 4) * 4;
-        const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        // three 512-byte row segments in flight per warp; a segment with no candidate (the common case once the threshold
-        // has risen) costs four compares and one vote
-        auto fetch = [&](int base) { const int c = base + lane * 4; return (base < c1v && c < c1v) ? *reinterpret_cast<const float4*>(row + c) : ninf; };
-        float4 n0 = fetch(c0), n1 = fetch(c0 + 128), n2 = fetch(c0 + 256);
-        for (int base = c0; base < c1v; base += 128) {
-            const int c = base + lane * 4;
-            const float4 v = n0;
-            n0 = n1; n1 = n2; n2 = fetch(base + 384);
-            const int g = c < c1v ? item_offset + c : -8;
-            const bool any = g >= 0 && (better(v.x, g, top.thr_v, top.thr_i) || better(v.y, g + 1, top.thr_v, top.thr_i) ||
-                                        better(v.z, g + 2, top.thr_v, top.thr_i) || better(v.w, g + 3, top.thr_v, top.thr_i));
-            if (!__any_sync(0xffffffffu, any)) continue;
-            top.offer(v.x, g);
-            top.offer(v.y, g + 1);
-            top.offer(v.z, g + 2);
-            top.offer(v.w, g + 3);
+    // [c0, cs): up to 3 scores before the first 16-byte boundary of the row (row strides need not be multiples of 4);
+    // [cs, c1v): the vector body; [c1v, c1): up to 3 tail scores
+    const int head = min(c1 - c0, (int)((4 - ((reinterpret_cast<uintptr_t>(row + c0) >> 2) & 3)) & 3));
+    const int cs = c0 + head;
+    const int c1v = cs + ((c1 - cs) / 4) * 4;
+    const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    auto fetch = [&](int base) { const int c = base + lane * 4; return (base < c1v && c < c1v) ? *reinterpret_cast<const float4*>(row + c) : ninf; };
+    float4 cur[kTopkSeg], nxt[kTopkSeg];
+#pragma unroll
+    for (int q = 0; q < kTopkSeg; ++q) cur[q] = fetch(cs + q * 128);
+    top.offer(lane < head ? row[c0 + lane] : -INFINITY, lane < head ? item_offset + c0 + lane : -1);
+    bool probe = K <= 32 && c1v - cs >= kTopkSeg * 128;
+    for (int base = cs; base < c1v; base += kTopkSeg * 128) {
+#pragma unroll
+        for (int q = 0; q < kTopkSeg; ++q) nxt[q] = fetch(base + kTopkSeg * 128 + q * 128);
+        float mq[kTopkSeg];
+#pragma unroll
+        for (int q = 0; q < kTopkSeg; ++q) mq[q] = fmaxf(fmaxf(cur[q].x, cur[q].y), fmaxf(cur[q].z, cur[q].w));
+        float m = mq[0];
+#pragma unroll
+        for (int q = 1; q < kTopkSeg; ++q) m = fmaxf(m, mq[q]);
+        if (probe) {        // first trip (all 1024 scores in range): seed the threshold from the lane maxima
+            probe = false;
+            int mi = -1;    // id of this lane's maximum (largest id among equals: the better pair)
+#pragma unroll
+            for (int q = 0; q < kTopkSeg; ++q) {
+                const int g = item_offset + base + q * 128 + lane * 4;
+                if (cur[q].x == m) mi = g;
+                if (cur[q].y == m) mi = g + 1;
+                if (cur[q].z == m) mi = g + 2;
+                if (cur[q].w == m) mi = g + 3;
+            }
+            int rank = 0;   // lanes holding a better pair (ids are distinct: a strict order)
+#pragma unroll
+            for (int o = 0; o < 32; ++o) rank += better(__shfl_sync(0xffffffffu, m, o), __shfl_sync(0xffffffffu, mi, o), m, mi) ? 1 : 0;
+            const int src = __ffs(__ballot_sync(0xffffffffu, rank == K - 1)) - 1;
+            if (src >= 0) top.raise(__shfl_sync(0xffffffffu, m, src), __shfl_sync(0xffffffffu, mi, src) - 1);   // "- 1": that pair itself is admitted
         }
-        { const int c = c1v + lane; top.offer(c < c1 ? row[c] : -INFINITY, c < c1 ? item_offset + c : -1); }    // <= 3 tail columns
-    } else {
-        for (int base = c0; base < c1; base += 32) {
-            const int c = base + lane;
-            top.offer(c < c1 ? row[c] : -INFINITY, c < c1 ? item_offset + c : -1);
+        if (__any_sync(0xffffffffu, m >= top.thr_v)) {
+#pragma unroll
+            for (int q = 0; q < kTopkSeg; ++q) {
+                const int c = base + q * 128 + lane * 4;
+                unsigned bal = __ballot_sync(0xffffffffu, c < c1v && mq[q] >= top.thr_v);
+                while (bal) {
+                    const int src = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    const int g = item_offset + base + q * 128 + src * 4;
+                    const float x = __shfl_sync(0xffffffffu, cur[q].x, src), y = __shfl_sync(0xffffffffu, cur[q].y, src);
+                    const float z = __shfl_sync(0xffffffffu, cur[q].z, src), w = __shfl_sync(0xffffffffu, cur[q].w, src);
+                    if (better(x, g, top.thr_v, top.thr_i)) top.insert(x, g);
+                    if (better(y, g + 1, top.thr_v, top.thr_i)) top.insert(y, g + 1);
+                    if (better(z, g + 2, top.thr_v, top.thr_i)) top.insert(z, g + 2);
+                    if (better(w, g + 3, top.thr_v, top.thr_i)) top.insert(w, g + 3);
+                }
+            }
         }
+#pragma unroll
+        for (int q = 0; q < kTopkSeg; ++q) cur[q] = nxt[q];
     }
+    { const int c = c1v + lane; top.offer(c < c1 ? row[c] : -INFINITY, c < c1 ? item_offset + c : -1); }    // <= 3 tail columns
     top.store(out_val + ((size_t)r * n_chunks + ch) * K, out_idx + ((size_t)r * n_chunks + ch) * K);
 }
 
@@ -352,9 +399,20 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_merge_kernel(const float
     if (r >= n_rows) return;
     WarpTopK top;
     top.init(K, lane, sv_all[warp], si_all[warp]);
-    for (int base = 0; base < GK; base += 32) {
-        const int j = base + lane;
-        top.offer(j < GK ? cval[(size_t)r * GK + j] : -INFINITY, j < GK ? cidx[(size_t)r * GK + j] : -1);
+    const float* cv = cval + (size_t)r * GK;
+    const int32_t* ci = cidx + (size_t)r * GK;
+    for (int base = 0; base < GK; base += 128) {       // four candidates per lane in flight
+        float v[4]; int id[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = base + q * 32 + lane;
+            v[q] = j < GK ? cv[j] : -INFINITY;
+            id[q] = j < GK ? ci[j] : -1;
+        }
+        const float tv = top.thr_v;
+        if (!__any_sync(0xffffffffu, v[0] >= tv || v[1] >= tv || v[2] >= tv || v[3] >= tv)) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) top.offer(v[q], id[q]);
     }
     top.store(out_val + (size_t)r * K, out_idx + (size_t)r * K);
 }
@@ -496,11 +554,13 @@ int hvae_candidate_rank(const void* U, int ldu, const void* E, int lde, int d, i
     return 0;
 }
 
-// Column chunks per row: enough (row, chunk) warps to fill the machine (~8k), chunks of at least 4096 scores, multiples of 128.
+// Column chunks per row.  Long chunks keep the scan on its fast path (see mask_topk_kernel), so a row is only cut when the
+// launch would otherwise have fewer warps than ~12 per SM, and never below 16k scores per chunk; multiples of 1024.
 static void topk_chunks(int n_rows, int N, int* n_chunks, int* chunk_len) {
-    int want = max(1, 8192 / max(1, n_rows));
-    int len = max(4096, ceil_div(N, want));
-    len = round_up(len, 128);
+    const int want_warps = 12 * kNumSMs;      // measured best at 256 x 1M (6: 63 %, 10: 71 %, 12: 72 %, 16: 51 % of HBM peak)
+    int nc = max(1, ceil_div(want_warps, max(1, n_rows)));
+    nc = max(1, min(nc, N / 16384));
+    const int len = round_up(ceil_div(N, nc), 1024);
     *chunk_len = len;
     *n_chunks = max(1, ceil_div(N, len));
 }
@@ -527,8 +587,8 @@ int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, co
                item_offset, indptr, indices, rows, exclude_seen, K, nc, len, cv, ci);
     HVAE_LAUNCH_CHECK("mask_topk");
     if (nc > 1) {
-        launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, (const float*)cand_val,
-                   (const int32_t*)cand_idx, n_rows, nc * K, K, out_val, out_idx);
+        launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, (const float*)cv,
+                   (const int32_t*)ci, n_rows, nc * K, K, out_val, out_idx);
         HVAE_LAUNCH_CHECK("mask_topk merge");
     }
     return 0;
@@ -537,8 +597,7 @@ int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, co
 int hvae_topk_merge(const float* cval, const int32_t* cidx, int n_rows, int GK, int K, float* out_val, int32_t* out_idx, void* stream) {
     HVAE_REQUIRE(K >= 1 && K <= kMaxK, "topk_merge: K=%d outside [1,%d]", K, kMaxK);
     if (n_rows == 0) return 0;
-    launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, cval, cidx, n_rows, GK, K, out_val,
-                                                                                                  out_idx);
+    launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, cval, cidx, n_rows, GK, K, out_val, out_idx);
     HVAE_LAUNCH_CHECK("topk_merge");
     return 0;
 }

@@ -83,7 +83,7 @@ def test_topk_order_and_masking(dev):
     lib = _cabi.lib()
     st = torch.cuda.current_stream().cuda_stream
     rng = np.random.default_rng(0)
-    for (R, N, K) in [(7, 1000, 20), (3, 37, 37), (5, 4099, 128), (4, 50, 50), (3, 70001, 20), (2, 40000, 100)]:
+    for (R, N, K) in [(7, 1000, 20), (3, 37, 37), (5, 4099, 128), (4, 50, 50), (3, 70001, 20), (2, 40000, 100), (300, 9000, 20), (64, 33000, 10), (5, 1_000_003, 32)]:
         S = rng.standard_normal((R, N)).astype(np.float32)
         S[:, ::7] = np.round(S[:, ::7], 1)           # plenty of exact ties
         seen_ptr, seen_idx = [0], []
