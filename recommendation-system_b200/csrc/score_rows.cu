@@ -102,7 +102,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                           const float* __restrict__ values, const int32_t* __restrict__ rows, int B,
                                                           const float* __restrict__ O, int ldo, int n_parts,
-                                                          const float* __restrict__ oscale, const T* __restrict__ E, int lde, int d,
+                                                          const float* __restrict__ oscale, const float* __restrict__ oscale2,
+                                                          const T* __restrict__ E, int lde, int d,
                                                           const float* __restrict__ inv_bg, float* __restrict__ dU, int lddu) {
     pdl_prologue();
     const int ld4 = lddu >> 2;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restr
     if (t >= B * ld4) return;
     const int b = t / ld4, c = (t - b * ld4) * 4;
     const int u = rows ? rows[b] : b;
-    const float ib = *inv_bg, s = oscale ? oscale[b] * ib : 1.0f;
+    const float ib = *inv_bg, s = oscale ? oscale[b] * (oscale2 ? oscale2[b] : 1.0f) * ib : 1.0f;
     const size_t pstride = (size_t)B * ldo;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* op = O + (size_t)b * ldo + c;
@@ -525,17 +526,17 @@ int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const fl
 }
 
 int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B, const float* O,
-                     int ldo, int n_parts, const float* oscale, const void* E, int lde, int d, int is_bf16, const float* inv_bg,
-                     float* dU, int lddu, void* stream) {
+                     int ldo, int n_parts, const float* oscale, const float* oscale2, const void* E, int lde, int d, int is_bf16,
+                     const float* inv_bg, float* dU, int lddu, void* stream) {
     if (B == 0) return 0;
     HVAE_REQUIRE(lddu % 4 == 0 && ldo % 4 == 0 && (!is_bf16 || lde % 8 == 0), "du_finalize: leading dimensions must be multiples of 4 (bf16 E: 8)");
     const int nb = ceil_div(B * (lddu / 4), 256);
     if (is_bf16)
         launch_pdl(du_finalize_kernel<__nv_bfloat16>, nb, 256, 0, (cudaStream_t)stream, 
-            indptr, indices, values, rows, B, O, ldo, n_parts, oscale, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
+            indptr, indices, values, rows, B, O, ldo, n_parts, oscale, oscale2, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
     else
         launch_pdl(du_finalize_kernel<float>, nb, 256, 0, (cudaStream_t)stream, indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
-                                                                                   (const float*)E, lde, d, inv_bg, dU, lddu);
+                   oscale2, (const float*)E, lde, d, inv_bg, dU, lddu);
     HVAE_LAUNCH_CHECK("du_finalize");
     return 0;
 }

@@ -42,7 +42,23 @@ struct StatsParams {
     const int64_t* indptr;   // seen items (CSR over users), may be null
     const int32_t* indices;
     const int32_t* rows;     // user ids of the batch rows (null = identity)
+    // gating of the two-pass fallback of hvae_tc_score_onepass (see GradParams): run only for flagged user tiles
+    const float* bound;
+    int gate;
 };
+
+// One-pass mode (hvae_tc_score_onepass): softmax numerators are taken against a fixed per-row shift instead of the row's
+// log-sum-exp, c_b = max(0, bound_b - kOnepassShift) with bound_b >= max_i |S_bi| (Cauchy-Schwarz, from the cast kernel).
+// exp(S - c) then lies in [e^-(2 bound - c), e^40]: for bound_b <= kOnepassMaxBound neither the largest term can overflow nor
+// the row's relevant terms underflow (fp32 and bf16 share the exponent range), so sum_i exp(S_bi - c_b) and
+// sum_i exp(S_bi - c_b) E_i are exact up to the usual rounding.  User tiles with a larger bound take the two-pass kernels.
+constexpr float kOnepassShift = 40.0f, kOnepassMaxBound = 55.0f;
+
+// CTA-uniform: does any of the tile's 128 rows carry a bound beyond the one-pass range?
+__device__ __forceinline__ bool tile_flagged(const float* bound, int m_tile, int B) {
+    const int rr = m_tile * 128 + (int)threadIdx.x;
+    return __syncthreads_or(threadIdx.x < 128 && rr < B && bound[rr] > kOnepassMaxBound) != 0;
+}
 
 struct __align__(8) PipeBarriers {
     uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
@@ -80,8 +96,11 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
+    const bool active = P.gate == 0 || tile_flagged(P.bound, m_tile, P.B);
 
-    if (warp == 0) {
+    if (!active) {
+        // fallback launch for a tile the one-pass kernel has handled: nothing to do
+    } else if (warp == 0) {
         if (lane == 0) {
             int it = 0;
             for (int t = t0; t < t1; ++t)
@@ -274,6 +293,41 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int co
     dst[i] = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
 }
 
+// Same cast, one warp per row, plus bound[r] = scale * ||bf16 row||_2 (slightly inflated): with scale = max_i ||E_i|| this is
+// an upper bound of |S_ri| for every item (Cauchy-Schwarz) -- the input of the one-pass scoring kernel's fixed shift.
+__global__ void __launch_bounds__(256) cast_bf16_bound_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
+                                                              __nv_bfloat16* __restrict__ dst, int ld_dst, float scale,
+                                                              float* __restrict__ bound) {
+    pdl_prologue();
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float ss = 0.f;
+    for (int c = lane; c < ld_dst; c += 32) {
+        const __nv_bfloat16 h = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
+        dst[(size_t)r * ld_dst + c] = h;
+        const float f = __bfloat162float(h);
+        ss = fmaf(f, f, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) bound[r] = scale * sqrtf(ss) * 1.002f + 1e-6f;
+}
+
+// After the one-pass kernel (and its gated two-pass fallback): lse_b = c_b + log sum_p l_part[p][b] and inv_l_b = 1 / sum for
+// the rows the one-pass kernel handled; rows of flagged tiles keep the lse the fallback published and get inv_l_b = 1.
+__global__ void __launch_bounds__(128) onepass_finalize_kernel(const float* __restrict__ bound, const float* __restrict__ l_part,
+                                                               int n_lparts, int B, float* __restrict__ lse, float* __restrict__ inv_l) {
+    pdl_prologue();
+    const bool flagged = tile_flagged(bound, blockIdx.x, B);
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= B) return;
+    if (flagged) { inv_l[b] = 1.0f; return; }
+    float l = 0.f;
+    for (int pp = 0; pp < n_lparts; ++pp) l += l_part[(size_t)pp * B + b];
+    lse[b] = fmaxf(0.f, bound[b] - kOnepassShift) + logf(l);
+    inv_l[b] = 1.0f / l;
+}
+
 
 // ----------------------------------------------------------------------------------------------------------------
 // Backward of the multinomial NLL through the scores: O[b,:] = sum_i softmax(S_b)_i * E_i, with S recomputed tile by
@@ -296,7 +350,43 @@ struct GradParams {
     float* lse_out;       // [B]
     float* Opart;         // [n_splits][B][ldo]
     int ldo;
+    // gate 0: two-pass mode above, every user tile.  gate 1: ONE-PASS mode -- numerators against the fixed shift
+    // max(0, bound - kOnepassShift), row sums of the numerators to l_part; tiles with a bound beyond kOnepassMaxBound are
+    // skipped.  gate 2: two-pass mode for exactly those skipped tiles.
+    const float* bound;   // [B]
+    int gate;
+    float* l_part;        // [n_splits * (2 if pair kernel else 1)][B]
 };
+
+// Softmax numerators of one [128 users x 128 items] score tile, thread <-> user row: p = exp2(v * log2e - shift2), packed to
+// bf16 and handed to store(item, w0..w3) in 16-byte groups of 8 items.  Returns the row's sum of the (unrounded) numerators
+// over the tile's first n_valid items (MASK: the catalogue ends inside this tile; TMA zero-fills the rows beyond it).
+template <bool MASK, class Store>
+__device__ __forceinline__ float softmax_tile(const float (&v)[4][32], float shift2, int n_valid, Store&& store) {
+    float lsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {         // 8 items -> one 16-byte chunk
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int idx = c * 32 + j8 * 8 + 2 * e;
+                float p0 = exp2f(fmaf(v[c][j8 * 8 + 2 * e], kLog2e, -shift2));
+                float p1 = exp2f(fmaf(v[c][j8 * 8 + 2 * e + 1], kLog2e, -shift2));
+                if (MASK) {
+                    if (idx >= n_valid) p0 = 0.f;
+                    if (idx + 1 >= n_valid) p1 = 0.f;
+                }
+                lsum += p0 + p1;
+                __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+                w[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            store(c * 32 + j8 * 8, w[0], w[1], w[2], w[3]);
+        }
+    }
+    return lsum;
+}
 
 struct __align__(8) GradBarriers {
     uint64_t full[G_STAGES], empty[G_STAGES], s_full, s_free, p_full[2], p_free[2], o_full;
@@ -337,8 +427,12 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
     const uint32_t tmem_base = bars->tmem_base;
     pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
     const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
+    const bool onepass = P.gate == 1;
+    const bool active = P.gate == 0 || tile_flagged(P.bound, m_tile, P.B) == (P.gate == 2);
 
-    if (warp == 0) {
+    if (!active) {
+        // this user tile belongs to the other mode's launch
+    } else if (warp == 0) {
         if (lane == 0) {
             int it = 0;
             auto acquire = [&](uint32_t bytes) {
@@ -421,9 +515,11 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
         const int r_local = q * 32 + lane;
         const int row = m_tile * BM + r_local;
         const bool row_ok = row < P.B;
-        float lse_row = 0.f;
+        float lse_row = 0.f;      // two-pass: the row's log-sum-exp; one-pass: the fixed shift
         if (row_ok) {
-            if (P.lse) {
+            if (onepass) {
+                lse_row = fmaxf(0.f, P.bound[row] - kOnepassShift);
+            } else if (P.lse) {
                 lse_row = P.lse[row];
             } else {   // merge the forward partials here instead of in a separate launch
                 const float* pm = P.part_m + (size_t)row * P.lse_splits;
@@ -438,6 +534,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
         }
         const float lse2 = lse_row * kLog2e;
         const uint32_t lane_base = uint32_t(q * 32) << 16;
+        float lsum = 0.f;
         for (int ti = 0; ti < T; ++ti) {
             const int pb = ti & 1;
             mbar_wait(&bars->s_full, ti & 1);
@@ -451,28 +548,19 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
             if (lane == 0) mbar_arrive(&bars->s_free);
             mbar_wait(&bars->p_free[pb], ((ti >> 1) & 1) ^ 1);
             uint8_t* prow = pbuf + pb * G_PBYTES + r_local * 128;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {         // 8 items -> one 16-byte chunk
-                    uint32_t w[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float p0 = exp2f(fmaf(v[c][j8 * 8 + 2 * e], kLog2e, -lse2));
-                        const float p1 = exp2f(fmaf(v[c][j8 * 8 + 2 * e + 1], kLog2e, -lse2));
-                        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-                        w[e] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                    const int item = c * 32 + j8 * 8;            // local item index 0..127
-                    const int atom = item >> 6, chunk16 = (item & 63) >> 3;
-                    uint8_t* dst = prow + atom * 16384 + ((chunk16 ^ (r_local & 7)) << 4);
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
+            auto store = [&](int item, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {   // item: local index 0..127
+                const int atom = item >> 6, chunk16 = (item & 63) >> 3;
+                uint8_t* dst = prow + atom * 16384 + ((chunk16 ^ (r_local & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, w2, w3);
+            };
+            const int n_valid = P.N - (t0 + ti) * G_BN;
+            if (n_valid >= G_BN) lsum += softmax_tile<false>(v, lse2, G_BN, store);
+            else lsum += softmax_tile<true>(v, lse2, n_valid, store);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->p_full[pb]);
         }
+        if (onepass && row_ok && chunk == 0) P.l_part[(size_t)split * P.B + row] = lsum;
         // ---- O (TMEM) -> global partial ---------------------------------------------------------------------
         mbar_wait(&bars->o_full, 0);
         tc_fence_after();
@@ -544,8 +632,12 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
     pdl_wait();
     const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
     auto own = [&](int ti) { return (uint32_t)(ti & 1) == rank; };
+    const bool onepass = P.gate == 1;
+    const bool active = P.gate == 0 || tile_flagged(P.bound, m_tile, P.B) == (P.gate == 2);   // same decision in both CTAs of the pair
 
-    if (warp == 0) {
+    if (!active) {
+        // this user tile belongs to the other mode's launch
+    } else if (warp == 0) {
         if (lane == 0) {
             int it = 0;
             auto acquire = [&](uint32_t bytes) {
@@ -631,9 +723,11 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
         const int r_local = q * 32 + lane;
         const int row = m_tile * BM + r_local;
         const bool row_ok = row < P.B;
-        float lse_row = 0.f;
+        float lse_row = 0.f;      // two-pass: the row's log-sum-exp; one-pass: the fixed shift
         if (row_ok) {
-            if (P.lse) {
+            if (onepass) {
+                lse_row = fmaxf(0.f, P.bound[row] - kOnepassShift);
+            } else if (P.lse) {
                 lse_row = P.lse[row];
             } else {
                 const float* pm = P.part_m + (size_t)row * P.lse_splits;
@@ -653,6 +747,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
         const uint32_t pfull_peer = map_to_cta(pfull_local, peer);
         const uint32_t prow_local = smem_u32(pbuf + pb * G_PBYTES + r_local * 128);
         const uint32_t prow_peer = map_to_cta(prow_local, peer);
+        float lsum = 0.f;
         for (int ti = (int)rank, k = 0; ti < T; ti += 2, ++k) {     // my tiles only
             mbar_wait(&bars->s_full, k & 1);
             tc_fence_after();
@@ -664,24 +759,14 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->s_free);
             mbar_wait_cluster(&bars->p_free[pb], (k & 1) ^ 1);      // both CTAs finished G2 of my previous tile
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float p0 = exp2f(fmaf(v[c][j8 * 8 + 2 * e], kLog2e, -lse2));
-                        const float p1 = exp2f(fmaf(v[c][j8 * 8 + 2 * e + 1], kLog2e, -lse2));
-                        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-                        w[e] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                    const int item = c * 32 + j8 * 8;
-                    const uint32_t off = (uint32_t)((item >> 6) * 16384 + ((((item & 63) >> 3) ^ (r_local & 7)) << 4));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_local + off), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                    st_cluster_v4(prow_peer + off, w[0], w[1], w[2], w[3]);
-                }
-            }
+            auto store = [&](int item, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+                const uint32_t off = (uint32_t)((item >> 6) * 16384 + ((((item & 63) >> 3) ^ (r_local & 7)) << 4));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_local + off), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+                st_cluster_v4(prow_peer + off, w0, w1, w2, w3);
+            };
+            const int n_valid = P.N - (t0 + ti) * G_BN;
+            if (n_valid >= G_BN) lsum += softmax_tile<false>(v, lse2, G_BN, store);
+            else lsum += softmax_tile<true>(v, lse2, n_valid, store);
             fence_proxy_async_all();
             __syncwarp();
             if (lane == 0) {
@@ -689,6 +774,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
                 mbar_arrive_cluster(pfull_peer);
             }
         }
+        if (onepass && row_ok) P.l_part[((size_t)split * 2 + rank) * P.B + row] = lsum;     // each CTA of the pair: its own tiles
         // ---- O (TMEM) -> global partial ---------------------------------------------------------------------
         mbar_wait(&bars->o_full, 0);
         tc_fence_after();
@@ -799,7 +885,7 @@ size_t hvae_tc_n_splits(int B, int N) { return (size_t)pick_splits(ceil_div(B, B
 size_t hvae_tc_topk_splits(int B, int N) { return (size_t)pick_topk_splits(ceil_div(B, BM), ceil_div(N, BN)); }
 
 static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* workspace, int* n_splits,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const float* bound = nullptr, int gate = 0) {
     CUtensorMap tmU, tmE;
     if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
     if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, BN)) return rc;
@@ -810,6 +896,7 @@ static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int ld
     P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
     P.part_m = workspace;
     P.part_l = workspace + (size_t)B * P.n_splits;
+    P.bound = bound; P.gate = gate;
     static bool attr_set = false;
     if (!attr_set) {
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
@@ -821,8 +908,14 @@ static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int ld
     return 0;
 }
 
+static bool grad_is_pair(int d) {
+    static const bool no_pair = getenv("HVAE_NO_PAIR") != nullptr;
+    return ceil_div(round_up(d, BK), G_DCHUNK) == 2 && !no_pair;
+}
+
 static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, const float* part_m,
-                       const float* part_l, int lse_splits, float* lse_out, float* Opart, int ldo, cudaStream_t stream) {
+                       const float* part_l, int lse_splits, float* lse_out, float* Opart, int ldo, cudaStream_t stream,
+                       const float* bound = nullptr, int gate = 0, float* l_part = nullptr) {
     HVAE_REQUIRE(ldo % 4 == 0 && ldo >= d, "tc_score_grad: bad ldo=%d for d=%d", ldo, d);
     CUtensorMap tmU, tmE;
     if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
@@ -831,6 +924,7 @@ static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, in
     GradParams P{};
     P.B = B; P.N = N; P.d = d; P.lse = lse; P.part_m = part_m; P.part_l = part_l; P.lse_splits = lse_splits; P.lse_out = lse_out;
     P.Opart = Opart; P.ldo = ldo;
+    P.bound = bound; P.gate = gate; P.l_part = l_part;
     P.n_splits = pick_grad_splits(m_tiles, n_chunks, n_tiles);
     P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
     static bool attr_set = false;
@@ -839,8 +933,7 @@ static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, in
         HVAE_CUDA(cudaFuncSetAttribute(score_grad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
         attr_set = true;
     }
-    static const bool no_pair = getenv("HVAE_NO_PAIR") != nullptr;
-    if (n_chunks == 2 && !no_pair) {      // the two column-chunk CTAs share the softmax tiles through DSMEM (cluster of 2 along y)
+    if (n_chunks == 2 && grad_is_pair(d)) {      // the two column-chunk CTAs share the softmax tiles through DSMEM (cluster of 2 along y)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(m_tiles, 2, P.n_splits);
         cfg.blockDim = dim3(192);
@@ -909,6 +1002,46 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
     return 0;
 }
 
+
+int hvae_cast_bf16_bound(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, float scale, float* bound,
+                         void* stream) {
+    if (rows == 0) return 0;
+    launch_pdl(cast_bf16_bound_kernel, ceil_div(rows, 8), 256, 0, (cudaStream_t)stream, src, rows, cols, ld_src, (__nv_bfloat16*)dst, ld_dst, scale,
+               bound);
+    HVAE_LAUNCH_CHECK("cast_bf16_bound");
+    return 0;
+}
+
+// floats: row-sum partials of the one-pass kernel + the (max, sum-exp) partials of the gated fallback
+size_t hvae_tc_onepass_workspace_floats(int B, int N, int d) {
+    const size_t gs = hvae_tc_grad_splits(B, N, d);
+    return (size_t)B * (2 * gs + 2 * hvae_tc_n_splits(B, N));
+}
+
+// Forward and backward through the scores in ONE sweep over the items (4 B N d executed flops instead of the 6 B N d of
+// hvae_tc_score_lse_grad): the backward kernel takes the softmax numerators against a fixed shift derived from `bound`
+// (hvae_cast_bf16_bound) and also returns their row sums.  Opart then holds UNNORMALISED sums: O = inv_l * sum_p Opart[p].
+// User tiles whose bound is outside the safe range run the two-pass kernels instead (same launch sequence every call, the
+// kernels of the mode a tile does not use exit at once), inv_l = 1 for their rows.
+int hvae_tc_score_onepass(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* bound, float* lse,
+                          float* inv_l, float* workspace, float* Opart, int ldo, void* stream) {
+    if (B == 0) return 0;
+    HVAE_REQUIRE(N > 0 && d > 0, "tc_score_onepass: empty catalogue");
+    const size_t gs = hvae_tc_grad_splits(B, N, d);
+    const int n_lparts = (int)gs * (grad_is_pair(d) ? 2 : 1);
+    float* l_part = workspace;
+    float* lse_ws = workspace + 2 * gs * (size_t)B;
+    if (int rc = launch_grad(U, ldu, B, E, lde, N, d, nullptr, nullptr, nullptr, 0, nullptr, Opart, ldo, (cudaStream_t)stream, bound, 1, l_part))
+        return rc;
+    int ns = 0;
+    if (int rc = launch_stats_lse(U, ldu, B, E, lde, N, d, lse_ws, &ns, (cudaStream_t)stream, bound, 2)) return rc;
+    if (int rc = launch_grad(U, ldu, B, E, lde, N, d, nullptr, lse_ws, lse_ws + (size_t)B * ns, ns, lse, Opart, ldo, (cudaStream_t)stream, bound, 2,
+                             nullptr))
+        return rc;
+    launch_pdl(onepass_finalize_kernel, ceil_div(B, 128), 128, 0, (cudaStream_t)stream, bound, (const float*)l_part, n_lparts, B, lse, inv_l);
+    HVAE_LAUNCH_CHECK("tc_score_onepass finalize");
+    return 0;
+}
 
 size_t hvae_tc_grad_splits(int B, int N, int d) {
     return (size_t)pick_grad_splits(ceil_div(B, BM), ceil_div(round_up(d, BK), G_DCHUNK), ceil_div(N, G_BN));

@@ -123,6 +123,77 @@ def test_tc_grad_matches_torch(dev, B, N, d):
     assert float((O - ref).abs().max()) < 1e-2 * scale + 1e-6        # against exact softmax: bf16 rounding of P
 
 
+def _onepass(lib, dev, U, E, st):
+    """-> (lse, O normalised [B, d], bound) of hvae_tc_score_onepass on the bf16-rounded operands."""
+    B, d = U.shape
+    N = E.shape[0]
+    Eb, lde = _cast(lib, E.contiguous(), dev)
+    emax = float(Eb.float().norm(dim=1).max())
+    ldu = _r8(d)
+    Ub = torch.empty(B, ldu, dtype=torch.bfloat16, device=dev)
+    bound = torch.empty(B, device=dev)
+    lib.cast_bf16_bound(U.contiguous().data_ptr(), B, d, d, Ub.data_ptr(), ldu, emax, bound.data_ptr(), st)
+    assert torch.equal(Ub[:, :d], U.to(torch.bfloat16)) and torch.all(Ub[:, d:] == 0)
+    S = Ub[:, :d].float().double() @ Eb[:, :d].float().double().t()
+    assert bool((bound.double() >= S.abs().max(dim=1).values).all())          # a true upper bound of every score
+    gs = int(lib.tc_grad_splits(B, N, d))
+    ldo = (d + 3) // 4 * 4
+    Op = torch.full((gs, B, ldo), float("nan"), device=dev)
+    lse = torch.full((B,), float("nan"), device=dev)
+    inv_l = torch.full((B,), float("nan"), device=dev)
+    ws = torch.empty(int(lib.tc_onepass_workspace_floats(B, N, d)), device=dev)
+    lib.tc_score_onepass(Ub.data_ptr(), ldu, B, Eb.data_ptr(), lde, N, d, bound.data_ptr(), lse.data_ptr(), inv_l.data_ptr(), ws.data_ptr(),
+                         Op.data_ptr(), ldo, st)
+    O = (Op.double().sum(0) * inv_l.double()[:, None])[:, :d]
+    return lse, O, bound, S, Eb[:, :d].float().double()
+
+
+@pytest.mark.parametrize("B,N,d", [(512, 12101, 384), (128, 256, 64), (77, 1000, 64), (300, 5000, 768), (130, 890, 384), (64, 300, 24),
+                                   (1, 513, 200), (256, 3000, 448), (200, 1100, 1000)])
+def test_tc_onepass_matches_torch(dev, B, N, d):
+    """Forward + backward through the scores in one sweep: lse and O = softmax(S) E from numerators against a fixed shift."""
+    from hvae_b200 import _cabi
+    lib = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    U, E = _operands(B, N, d, dev, seed=2)
+    lse, O, bound, S, Ed = _onepass(lib, dev, U, E, st)
+    assert float(bound.max()) < 55.0                                          # every tile on the one-pass kernel
+    np.testing.assert_allclose(lse.cpu().numpy(), torch.logsumexp(S, dim=1).cpu().numpy(), rtol=2e-6, atol=2e-5)
+    Pm = torch.softmax(S, dim=1)
+    ref = Pm @ Ed
+    scale = float(ref.abs().max())
+    assert torch.isfinite(O).all()
+    assert float((O - ref).abs().max()) < 1e-2 * scale + 1e-6                 # bf16 rounding of the numerators
+
+
+def test_tc_onepass_shift_and_fallback(dev):
+    """Rows with large norms: bound in (40, 55] exercises a non-zero shift, bound > 55 sends that user tile (and only it) to
+    the two-pass kernels inside the same call; peaked and flat rows in one batch."""
+    from hvae_b200 import _cabi
+    lib = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    for d, N in ((384, 3001), (768, 2500)):
+        B = 300                                                               # three user tiles
+        U, E = _operands(B, N, d, dev, seed=5)
+        U = U / U.norm(dim=1, keepdim=True)
+        norms = torch.full((B,), 6.0, device=dev)
+        norms[3] = 48.0                                                       # tile 0: shifted, still one-pass
+        norms[130] = 300.0                                                    # tile 1: beyond the range -> two-pass fallback
+        norms[131] = 90.0
+        norms[260] = 0.0                                                      # tile 2: an all-zero user vector (uniform softmax)
+        U = U * norms[:, None]
+        U[5] = 45.0 * E[17]                                                   # aligned with an item: a very peaked row
+        lse, O, bound, S, Ed = _onepass(lib, dev, U, E, st)
+        flagged = (bound.view(-1)[:256].view(2, 128) > 55.0).any(dim=1).cpu().tolist()
+        assert flagged == [False, True] and not bool((bound[256:] > 55.0).any())
+        ref_lse = torch.logsumexp(S, dim=1)
+        np.testing.assert_allclose(lse.cpu().numpy(), ref_lse.cpu().numpy(), rtol=3e-6, atol=5e-5)
+        ref = torch.softmax(S, dim=1) @ Ed
+        assert torch.isfinite(O).all()
+        err = (O - ref).abs().max(dim=1).values
+        assert float(err.max()) < 1e-2 * float(ref.abs().max()) + 1e-6
+
+
 def test_gemm_tf32_all_layouts(dev):
     """tcgen05 kind::tf32 GEMM: every transpose combination the MLP forward/backward uses, ragged sizes, bias, alpha."""
     from hvae_b200 import _cabi
