@@ -299,6 +299,12 @@ def main():
         kernels["score_bwd"] = {"ms": span_avg["score_bwd"], "bound": "tensor", "achieved": flops_fwd / (span_avg["score_bwd"] * 1e-3) / 1e12,
                                 "peak": pk["tc_sustained"], "unit": "TFLOP/s", "algorithmic_flops": flops_fwd,
                                 "executed_flops": flops_fwd * (1 + -(-((d + 63) // 64 * 64) // 384))}
+    if "score_onepass" in span_avg:     # forward + backward through the scores in one sweep: S = U E^T and O = P E, 2BNd each
+        kernels["score_onepass"] = {"ms": span_avg["score_onepass"], "bound": "tensor",
+                                    "achieved": 2 * flops_fwd / (span_avg["score_onepass"] * 1e-3) / 1e12, "peak": pk["tc_sustained"],
+                                    "unit": "TFLOP/s", "algorithmic_flops": 2 * flops_fwd,
+                                    "executed_flops": flops_fwd * (2 if d <= 768 else 1 + -(-((d + 63) // 64 * 64) // 384)),
+                                    "launches": "one-pass kernel + gated two-pass fallback (idle) + finalize"}
     if "gather" in span_avg:
         nnz_avg = float(lens[order[:Bg * min(4, n_batches)]].sum()) / min(4, n_batches) / world
         gbytes = nnz_avg * (ld1 * 4 + 4) + B * (3 * ld1 * 4 + 16)
@@ -316,7 +322,8 @@ def main():
         kd = kernels[dom]
         roofline = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"],
                     "frac": kd["frac"], "traffic": traffic, "peak_source": pk["source"] + (" sustained" if kd["bound"] == "tensor" else ""),
-                    "ms_per_launch": kd["ms"], "share_of_step": kd["ms"] / max(1e-9, sum(span_avg.values()))}
+                    "ms_per_launch": kd["ms"],
+                    "share_of_step": kd["ms"] / max(1e-9, sum(v for k, v in span_avg.items() if not k.startswith("score_")))}
 
     # ---- timed region 2 (`e2e`): public API with HOST (pinned) batches; H2D of the batch and D2H of the loss every step
     KE = min(K, 200)

@@ -123,12 +123,14 @@ int hvae_row_softmax_scale(float* S, int64_t lds, int rows, int N, const float* 
 int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
                          const void* U, int ldu, const void* E, int lde, int d, int is_bf16, float* dot, float* xsum,
                          void* stream);
-/* dU = s_b * sum_p O[p] - (1/Bg) * sum_j x_bj E_idx_j;  O: n_parts partial sums [n_parts][B][ldo];
- * s_b = oscale ? oscale[b]*(oscale2 ? oscale2[b] : 1)/Bg : 1 (oscale = row sums |x|_b when O holds softmax-weighted sums;
- * oscale2 = inv_l of hvae_tc_score_onepass when they are unnormalised). */
+/* dU = s_b * O_b - (1/Bg) * sum_j x_bj E_idx_j;  O: n_parts partial sums [n_parts][B][ldo];
+ * s_b = oscale ? oscale[b]/Bg : 1 (oscale = row sums |x|_b when O holds softmax-weighted sums).
+ * O_b = sum_p O[p][b], or, with the unnormalised partials of hvae_tc_score_onepass (c_part != NULL),
+ * O_b = sum_p e^{c_p} O[p][b] / sum_p e^{c_p} sum_sub l_part[p][sub][b]. */
 int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
-                     const float* O, int ldo, int n_parts, const float* oscale, const float* oscale2, const void* E, int lde,
-                     int d, int is_bf16, const float* inv_bg, float* dU, int lddu, void* stream);
+                     const float* O, int ldo, int n_parts, const float* oscale, const float* c_part, const float* l_part,
+                     int n_sub, const void* E, int lde, int d, int is_bf16, const float* inv_bg, float* dU, int lddu,
+                     void* stream);
 /* Seen-item masking (in place) + top-K of materialised scores under the order (score desc, index desc).  Rows are cut into
  * hvae_mask_topk_chunks(n_rows, N) column chunks; cand_val / cand_idx: scratch [n_rows, chunks * K] (NULL if chunks == 1). */
 size_t hvae_mask_topk_chunks(int n_rows, int N);
@@ -175,17 +177,19 @@ int hvae_tc_score_grad(const void* U, int ldu, int B, const void* E, int lde, in
 int hvae_tc_score_lse_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* lse, float* workspace,
                            float* Opart, int ldo, void* stream);
 
-/* Forward + backward through the scores in one sweep over the items (what a training step uses): softmax numerators are
- * taken against a fixed per-row shift derived from bound[b] >= max_i |S_bi| instead of the log-sum-exp, so no forward
- * pass is needed first.  hvae_cast_bf16_bound: hvae_cast_bf16 plus bound[r] = scale * ||row r||_2 (scale = max_i ||E_i||).
- * Out: lse [B]; inv_l [B]; Opart [hvae_tc_grad_splits][B][ldo] UNNORMALISED partial sums, O_b = inv_l[b] * sum_p Opart[p][b].
- * Rows whose bound is outside the range the shift covers (> 55) take the two-pass kernels inside the same call.
- * workspace >= hvae_tc_onepass_workspace_floats(B, N, d) floats. */
-int hvae_cast_bf16_bound(const float* src, int rows, int cols, int ld_src, void* dst_bf16, int ld_dst, float scale,
-                         float* bound, void* stream);
-size_t hvae_tc_onepass_workspace_floats(int B, int N, int d);
-int hvae_tc_score_onepass(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* bound,
-                          float* lse, float* inv_l, float* workspace, float* Opart, int ldo, void* stream);
+/* Forward + backward through the scores in ONE sweep over the items (what a training step uses; 4BNd executed flops instead
+ * of 6BNd): softmax numerators are taken against a per-row shift known before the sweep -- the row's best score among the
+ * first 8 items (hvae_cast_bf16_probe = hvae_cast_bf16 + that shift), a lower bound of its largest score, so nothing relevant
+ * underflows; a row whose numerators overflow makes its CTA repeat the sweep with shift + 60.
+ * Out: Opart [S = hvae_tc_grad_splits(B,N,d)][B][ldo] UNNORMALISED partial sums; c_part [S][B] the shift each split ended up
+ * with; l_part [S][n_sub = hvae_tc_onepass_subparts(d)][B] row sums of the numerators.  hvae_du_finalize combines them
+ * (O_b = sum_p e^{c_p} Opart[p][b] / sum_p e^{c_p} l_p), hvae_tc_onepass_lse gives lse_b = log sum_p e^{c_p} l_p. */
+int hvae_cast_bf16_probe(const float* src, int rows, int cols, int ld_src, void* dst_bf16, int ld_dst, const void* E, int lde,
+                         int N, float* shift, void* stream);
+size_t hvae_tc_onepass_subparts(int d);
+int hvae_tc_score_onepass(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* shift,
+                          float* c_part, float* l_part, float* Opart, int ldo, void* stream);
+int hvae_tc_onepass_lse(const float* c_part, const float* l_part, int n_parts, int n_sub, int B, float* lse, void* stream);
 
 /* ---- optimiser (train.py:63,88-92; model.py:312-323) --------------------------------------------------- */
 /* advance != 0: a training step (Adam step count, annealing step and the noise counter (+= noise_stride) move on) */

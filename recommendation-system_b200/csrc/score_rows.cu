@@ -102,7 +102,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                           const float* __restrict__ values, const int32_t* __restrict__ rows, int B,
                                                           const float* __restrict__ O, int ldo, int n_parts,
-                                                          const float* __restrict__ oscale, const float* __restrict__ oscale2,
+                                                          const float* __restrict__ oscale, const float* __restrict__ c_part,
+                                                          const float* __restrict__ l_part, int n_sub,
                                                           const T* __restrict__ E, int lde, int d,
                                                           const float* __restrict__ inv_bg, float* __restrict__ dU, int lddu) {
     pdl_prologue();
@@ -111,13 +112,29 @@ __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restr
     if (t >= B * ld4) return;
     const int b = t / ld4, c = (t - b * ld4) * 4;
     const int u = rows ? rows[b] : b;
-    const float ib = *inv_bg, s = oscale ? oscale[b] * (oscale2 ? oscale2[b] : 1.0f) * ib : 1.0f;
+    const float ib = *inv_bg;
+    float s = oscale ? oscale[b] * ib : 1.0f;
     const size_t pstride = (size_t)B * ldo;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* op = O + (size_t)b * ldo + c;
-    for (int pp = 0; pp < n_parts; ++pp) {
-        const float4 v = *reinterpret_cast<const float4*>(op + pp * pstride);
-        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+    if (c_part) {       // unnormalised partials of the one-pass scoring kernel: weights e^{c_p - M}, normalised by their numerator sums
+        float M = -INFINITY;
+        for (int pp = 0; pp < n_parts; ++pp) M = fmaxf(M, c_part[(size_t)pp * B + b]);
+        float D = 0.f;
+        for (int pp = 0; pp < n_parts; ++pp) {
+            const float e = expf(c_part[(size_t)pp * B + b] - M);
+            float l = 0.f;
+            for (int sb = 0; sb < n_sub; ++sb) l += l_part[((size_t)pp * n_sub + sb) * B + b];
+            D = fmaf(e, l, D);
+            const float4 v = *reinterpret_cast<const float4*>(op + pp * pstride);
+            o.x = fmaf(e, v.x, o.x); o.y = fmaf(e, v.y, o.y); o.z = fmaf(e, v.z, o.z); o.w = fmaf(e, v.w, o.w);
+        }
+        s /= D;
+    } else {
+        for (int pp = 0; pp < n_parts; ++pp) {
+            const float4 v = *reinterpret_cast<const float4*>(op + pp * pstride);
+            o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+        }
     }
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t js = indptr[u], je = indptr[u + 1];
@@ -526,17 +543,17 @@ int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const fl
 }
 
 int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B, const float* O,
-                     int ldo, int n_parts, const float* oscale, const float* oscale2, const void* E, int lde, int d, int is_bf16,
-                     const float* inv_bg, float* dU, int lddu, void* stream) {
+                     int ldo, int n_parts, const float* oscale, const float* c_part, const float* l_part, int n_sub, const void* E, int lde,
+                     int d, int is_bf16, const float* inv_bg, float* dU, int lddu, void* stream) {
     if (B == 0) return 0;
     HVAE_REQUIRE(lddu % 4 == 0 && ldo % 4 == 0 && (!is_bf16 || lde % 8 == 0), "du_finalize: leading dimensions must be multiples of 4 (bf16 E: 8)");
     const int nb = ceil_div(B * (lddu / 4), 256);
     if (is_bf16)
         launch_pdl(du_finalize_kernel<__nv_bfloat16>, nb, 256, 0, (cudaStream_t)stream, 
-            indptr, indices, values, rows, B, O, ldo, n_parts, oscale, oscale2, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
+            indptr, indices, values, rows, B, O, ldo, n_parts, oscale, c_part, l_part, n_sub, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
     else
         launch_pdl(du_finalize_kernel<float>, nb, 256, 0, (cudaStream_t)stream, indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
-                   oscale2, (const float*)E, lde, d, inv_bg, dU, lddu);
+                   c_part, l_part, n_sub, (const float*)E, lde, d, inv_bg, dU, lddu);
     HVAE_LAUNCH_CHECK("du_finalize");
     return 0;
 }

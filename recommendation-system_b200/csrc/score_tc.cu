@@ -42,23 +42,14 @@ struct StatsParams {
     const int64_t* indptr;   // seen items (CSR over users), may be null
     const int32_t* indices;
     const int32_t* rows;     // user ids of the batch rows (null = identity)
-    // gating of the two-pass fallback of hvae_tc_score_onepass (see GradParams): run only for flagged user tiles
-    const float* bound;
-    int gate;
 };
 
-// One-pass mode (hvae_tc_score_onepass): softmax numerators are taken against a fixed per-row shift instead of the row's
-// log-sum-exp, c_b = max(0, bound_b - kOnepassShift) with bound_b >= max_i |S_bi| (Cauchy-Schwarz, from the cast kernel).
-// exp(S - c) then lies in [e^-(2 bound - c), e^40]: for bound_b <= kOnepassMaxBound neither the largest term can overflow nor
-// the row's relevant terms underflow (fp32 and bf16 share the exponent range), so sum_i exp(S_bi - c_b) and
-// sum_i exp(S_bi - c_b) E_i are exact up to the usual rounding.  User tiles with a larger bound take the two-pass kernels.
-constexpr float kOnepassShift = 40.0f, kOnepassMaxBound = 55.0f;
-
-// CTA-uniform: does any of the tile's 128 rows carry a bound beyond the one-pass range?
-__device__ __forceinline__ bool tile_flagged(const float* bound, int m_tile, int B) {
-    const int rr = m_tile * 128 + (int)threadIdx.x;
-    return __syncthreads_or(threadIdx.x < 128 && rr < B && bound[rr] > kOnepassMaxBound) != 0;
-}
+// One-pass mode (hvae_tc_score_onepass): softmax numerators are taken against a per-row shift c_b that is known BEFORE the
+// sweep instead of the row's log-sum-exp: c_b = max of the row's scores against a few probe items (cast kernel), hence
+// c_b <= max_i S_bi and the row's largest numerator is >= 1 -- nothing relevant can underflow.  The other direction is
+// checked: a row whose numerators sum beyond kOnepassOverflow (or to inf) repeats the sweep with c_b + kOnepassRetry.
+// fp32 and bf16 share the exponent range, so sum_i exp(S_bi - c_b) and sum_i exp(S_bi - c_b) E_i lose nothing.
+constexpr float kOnepassRetry = 60.0f, kOnepassOverflow = 1.2676506e30f /* 2^100 */;
 
 struct __align__(8) PipeBarriers {
     uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
@@ -96,11 +87,8 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
-    const bool active = P.gate == 0 || tile_flagged(P.bound, m_tile, P.B);
 
-    if (!active) {
-        // fallback launch for a tile the one-pass kernel has handled: nothing to do
-    } else if (warp == 0) {
+    if (warp == 0) {
         if (lane == 0) {
             int it = 0;
             for (int t = t0; t < t1; ++t)
@@ -293,39 +281,57 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int co
     dst[i] = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
 }
 
-// Same cast, one warp per row, plus bound[r] = scale * ||bf16 row||_2 (slightly inflated): with scale = max_i ||E_i|| this is
-// an upper bound of |S_ri| for every item (Cauchy-Schwarz) -- the input of the one-pass scoring kernel's fixed shift.
-__global__ void __launch_bounds__(256) cast_bf16_bound_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
-                                                              __nv_bfloat16* __restrict__ dst, int ld_dst, float scale,
-                                                              float* __restrict__ bound) {
+// Same cast, one warp per row, plus shift[r] = max_j <bf16 row r, E_j> over the first n_probe items: a lower bound of the row's
+// largest score, the fixed softmax shift of the one-pass scoring kernel (see kOnepassRetry above).
+constexpr int kMaxProbe = 8;
+__global__ void __launch_bounds__(256) cast_bf16_probe_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
+                                                              __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                                              const __nv_bfloat16* __restrict__ E, int lde, int n_probe,
+                                                              float* __restrict__ shift) {
     pdl_prologue();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= rows) return;
-    float ss = 0.f;
+    float acc[kMaxProbe];
+#pragma unroll
+    for (int j = 0; j < kMaxProbe; ++j) acc[j] = 0.f;
     for (int c = lane; c < ld_dst; c += 32) {
         const __nv_bfloat16 h = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
         dst[(size_t)r * ld_dst + c] = h;
         const float f = __bfloat162float(h);
-        ss = fmaf(f, f, ss);
-    }
+        if (c < cols) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) bound[r] = scale * sqrtf(ss) * 1.002f + 1e-6f;
+            for (int j = 0; j < kMaxProbe; ++j)
+                if (j < n_probe) acc[j] = fmaf(f, __bfloat162float(E[(size_t)j * lde + c]), acc[j]);
+        }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMaxProbe; ++j) {
+        float a = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (j < n_probe) m = fmaxf(m, a);
+    }
+    if (lane == 0) shift[r] = n_probe > 0 ? m : 0.f;
 }
 
-// After the one-pass kernel (and its gated two-pass fallback): lse_b = c_b + log sum_p l_part[p][b] and inv_l_b = 1 / sum for
-// the rows the one-pass kernel handled; rows of flagged tiles keep the lse the fallback published and get inv_l_b = 1.
-__global__ void __launch_bounds__(128) onepass_finalize_kernel(const float* __restrict__ bound, const float* __restrict__ l_part,
-                                                               int n_lparts, int B, float* __restrict__ lse, float* __restrict__ inv_l) {
+// lse of the one-pass kernel's per-split results (shift c_p, numerator sums l_part[p][sub]) of every row:
+// lse_b = M + log sum_p exp(c_p - M) sum_sub l_part, M = max_p c_p (all c_p are equal unless a split had to repeat its sweep).
+// hvae_du_finalize applies the same weights to the unnormalised O partials.
+__global__ void __launch_bounds__(128) onepass_lse_kernel(const float* __restrict__ c_part, const float* __restrict__ l_part,
+                                                          int n_parts, int n_sub, int B, float* __restrict__ lse) {
     pdl_prologue();
-    const bool flagged = tile_flagged(bound, blockIdx.x, B);
     const int b = blockIdx.x * 128 + threadIdx.x;
     if (b >= B) return;
-    if (flagged) { inv_l[b] = 1.0f; return; }
-    float l = 0.f;
-    for (int pp = 0; pp < n_lparts; ++pp) l += l_part[(size_t)pp * B + b];
-    lse[b] = fmaxf(0.f, bound[b] - kOnepassShift) + logf(l);
-    inv_l[b] = 1.0f / l;
+    float M = -INFINITY;
+    for (int pp = 0; pp < n_parts; ++pp) M = fmaxf(M, c_part[(size_t)pp * B + b]);
+    float D = 0.f;
+    for (int pp = 0; pp < n_parts; ++pp) {
+        float l = 0.f;
+        for (int sb = 0; sb < n_sub; ++sb) l += l_part[((size_t)pp * n_sub + sb) * B + b];
+        D = fmaf(expf(c_part[(size_t)pp * B + b] - M), l, D);
+    }
+    lse[b] = M + logf(D);
 }
 
 
@@ -335,6 +341,8 @@ __global__ void __launch_bounds__(128) onepass_finalize_kernel(const float* __re
 // 128-item tile:  G1: S = U E_t^T (K = d, accumulators in TMEM)  ->  registers: P = exp(S - lse_b) -> bf16 -> smem
 // (128B-swizzled, K-major)  ->  G2: O += P E_t (K = 128 items; B operand = the same E rows read MN-major).
 // One CTA = (128 users, <=384 columns of O, a range of item tiles).  No gradient for E (frozen buffer).
+// One-pass mode (P.shift != null): the same sweep also IS the forward pass -- numerators against the fixed shift, their row
+// sums to l_part, O left unnormalised; a row that overflows makes its CTA (pair) repeat the sweep with a larger shift.
 constexpr int G_BN = 128;                     // items per tile
 constexpr int G_STAGES = 4, G_SLOT = 32768;   // ring slot: U [128x64] + E [128x64] for G1, or E [64 x <=256] for G2
 constexpr int G_DCHUNK = 384;                 // O columns per CTA (TMEM: 384 O + 128 S = 512)
@@ -350,12 +358,10 @@ struct GradParams {
     float* lse_out;       // [B]
     float* Opart;         // [n_splits][B][ldo]
     int ldo;
-    // gate 0: two-pass mode above, every user tile.  gate 1: ONE-PASS mode -- numerators against the fixed shift
-    // max(0, bound - kOnepassShift), row sums of the numerators to l_part; tiles with a bound beyond kOnepassMaxBound are
-    // skipped.  gate 2: two-pass mode for exactly those skipped tiles.
-    const float* bound;   // [B]
-    int gate;
-    float* l_part;        // [n_splits * (2 if pair kernel else 1)][B]
+    // one-pass mode
+    const float* shift;   // [B] initial shift per row (<= the row's largest score), or null = two-pass mode above
+    float* c_part;        // [n_splits][B]  shift finally used by the split
+    float* l_part;        // [n_splits][n_sub][B]  row sums of the numerators (n_sub = 2 for the pair kernel: one per CTA)
 };
 
 // Softmax numerators of one [128 users x 128 items] score tile, thread <-> user row: p = exp2(v * log2e - shift2), packed to
@@ -391,7 +397,19 @@ __device__ __forceinline__ float softmax_tile(const float (&v)[4][32], float shi
 struct __align__(8) GradBarriers {
     uint64_t full[G_STAGES], empty[G_STAGES], s_full, s_free, p_full[2], p_free[2], o_full;
     uint32_t tmem_base;
+    uint8_t retry[2][BM];     // pair kernel: per-row "sweep overflowed" flags of both CTAs (each CTA holds both arrays)
 };
+
+// Row r of the merged forward partials (two-pass mode without a ready lse).
+__device__ __forceinline__ float merged_lse(const float* part_m, const float* part_l, int lse_splits, int row) {
+    const float* pm = part_m + (size_t)row * lse_splits;
+    const float* pl = part_l + (size_t)row * lse_splits;
+    float M = -INFINITY;
+    for (int sp = 0; sp < lse_splits; ++sp) M = fmaxf(M, pm[sp]);
+    float l = 0.f;
+    for (int sp = 0; sp < lse_splits; ++sp) l += pl[sp] * expf(pm[sp] - M);
+    return M + logf(l);
+}
 
 __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constant__ CUtensorMap tmU,
                                                             const __grid_constant__ CUtensorMap tmE, GradParams P) {
@@ -427,143 +445,148 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
     const uint32_t tmem_base = bars->tmem_base;
     pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
     const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
-    const bool onepass = P.gate == 1;
-    const bool active = P.gate == 0 || tile_flagged(P.bound, m_tile, P.B) == (P.gate == 2);
+    const bool onepass = P.shift != nullptr;
 
-    if (!active) {
-        // this user tile belongs to the other mode's launch
-    } else if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            auto acquire = [&](uint32_t bytes) {
-                const int s = it % G_STAGES;
-                mbar_wait(&bars->empty[s], ((it / G_STAGES) & 1) ^ 1);
-                mbar_expect_tx(&bars->full[s], bytes);
-                ++it;
-                return s;
-            };
-            for (int ti = 0; ti <= T; ++ti) {
-                if (ti < T) {          // G1 operands of tile ti
-                    const int item0 = (t0 + ti) * G_BN;
-                    for (int kb = 0; kb < KB; ++kb) {
-                        const int s = acquire(G_SLOT);
-                        uint8_t* slot = smem + s * G_SLOT;
-                        tma_load_2d(slot, &tmU, kb * BK, m_tile * BM, &bars->full[s]);
-                        tma_load_2d(slot + 16384, &tmE, kb * BK, item0, &bars->full[s]);
-                        tma_load_2d(slot + 16384 + 8192, &tmE, kb * BK, item0 + 64, &bars->full[s]);
-                    }
-                }
-                if (ti >= 1) {         // G2 operands of tile ti-1: E rows as [64 items x (<=256 columns)] blocks
-                    const int item0 = (t0 + ti - 1) * G_BN;
-                    for (int ih = 0; ih < 2; ++ih)
-                        for (int g = 0; g < NG; ++g) {
-                            const int nb = min(4, (DC - g * 256) / 64);
-                            const int s = acquire(nb * 8192);
+    // epilogue state (warps 2..5): thread <-> user row
+    const int q = warp & 3;
+    const int r_local = q * 32 + lane;
+    const int row = m_tile * BM + r_local;
+    const bool row_ok = warp >= 2 && row < P.B;
+    const uint32_t lane_base = uint32_t(q * 32) << 16;
+    float lse_row = 0.f;      // two-pass: the row's log-sum-exp; one-pass: the shift
+    if (row_ok) {
+        if (onepass) lse_row = P.shift[row];
+        else if (P.lse) lse_row = P.lse[row];
+        else {                 // merge the forward partials here instead of in a separate launch
+            lse_row = merged_lse(P.part_m, P.part_l, P.lse_splits, row);
+            if (chunk == 0 && split == 0) P.lse_out[row] = lse_row;
+        }
+    }
+    float lsum = 0.f;
+    int it = 0;               // ring position of the producer / the MMA issuer; runs on across sweeps
+    // A sweep = all tiles of this CTA.  Barrier phases are derived from g = sweep * T + tile, so that a repeated sweep
+    // (one-pass mode, after an overflow) simply continues the sequences.
+    for (int sweep = 0;; ++sweep) {
+        if (warp == 0) {
+            if (lane == 0) {
+                auto acquire = [&](uint32_t bytes) {
+                    const int s = it % G_STAGES;
+                    mbar_wait(&bars->empty[s], ((it / G_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&bars->full[s], bytes);
+                    ++it;
+                    return s;
+                };
+                for (int ti = 0; ti <= T; ++ti) {
+                    if (ti < T) {          // G1 operands of tile ti
+                        const int item0 = (t0 + ti) * G_BN;
+                        for (int kb = 0; kb < KB; ++kb) {
+                            const int s = acquire(G_SLOT);
                             uint8_t* slot = smem + s * G_SLOT;
-                            for (int j = 0; j < nb; ++j)
-                                tma_load_2d(slot + j * 8192, &tmE, dc0 + g * 256 + j * 64, item0 + ih * 64, &bars->full[s]);
+                            tma_load_2d(slot, &tmU, kb * BK, m_tile * BM, &bars->full[s]);
+                            tma_load_2d(slot + 16384, &tmE, kb * BK, item0, &bars->full[s]);
+                            tma_load_2d(slot + 16384 + 8192, &tmE, kb * BK, item0 + 64, &bars->full[s]);
                         }
+                    }
+                    if (ti >= 1) {         // G2 operands of tile ti-1: E rows as [64 items x (<=256 columns)] blocks
+                        const int item0 = (t0 + ti - 1) * G_BN;
+                        for (int ih = 0; ih < 2; ++ih)
+                            for (int g = 0; g < NG; ++g) {
+                                const int nb = min(4, (DC - g * 256) / 64);
+                                const int s = acquire(nb * 8192);
+                                uint8_t* slot = smem + s * G_SLOT;
+                                for (int j = 0; j < nb; ++j)
+                                    tma_load_2d(slot + j * 8192, &tmE, dc0 + g * 256 + j * 64, item0 + ih * 64, &bars->full[s]);
+                            }
+                    }
                 }
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = make_idesc(BM, G_BN, 0, 0);
-            int it = 0;
-            for (int ti = 0; ti <= T; ++ti) {
-                if (ti < T) {          // G1(ti): S = U E_t^T
-                    mbar_wait(&bars->s_free, (ti & 1) ^ 1);
-                    tc_fence_after();
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        const int s = it % G_STAGES;
-                        mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc1 = make_idesc(BM, G_BN, 0, 0);
+                for (int ti = 0; ti <= T; ++ti) {
+                    if (ti < T) {          // G1(ti): S = U E_t^T
+                        const int g = sweep * T + ti;
+                        mbar_wait(&bars->s_free, (g & 1) ^ 1);
                         tc_fence_after();
-                        const uint32_t a0 = smem_u32(smem + s * G_SLOT), b0 = a0 + 16384;
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            umma_ss(tmem_S, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc1, (kb | k) != 0);
-                        umma_commit(&bars->empty[s]);
-                    }
-                    umma_commit(&bars->s_full);
-                }
-                if (ti >= 1) {         // G2(ti-1): O += P E_t
-                    const int tj = ti - 1, pb = tj & 1;
-                    mbar_wait(&bars->p_full[pb], (tj >> 1) & 1);
-                    tc_fence_after();
-                    const uint32_t p0 = smem_u32(pbuf + pb * G_PBYTES);
-                    for (int ih = 0; ih < 2; ++ih)
-                        for (int g = 0; g < NG; ++g, ++it) {
-                            const int ncols = min(256, DC - g * 256);
-                            const uint32_t idesc2 = make_idesc(BM, ncols, 0, 1);
+                        for (int kb = 0; kb < KB; ++kb, ++it) {
                             const int s = it % G_STAGES;
                             mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
                             tc_fence_after();
-                            const uint32_t b0 = smem_u32(smem + s * G_SLOT);
+                            const uint32_t a0 = smem_u32(smem + s * G_SLOT), b0 = a0 + 16384;
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)      // K = 16 items per MMA
-                                umma_ss(tmem_O + g * 256, make_desc(p0 + ih * 16384 + kk * 32, 16, 1024),
-                                        make_desc(b0 + kk * 2048, 8192, 1024), idesc2, (tj | ih | kk) != 0);
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_ss(tmem_S, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc1, (kb | k) != 0);
                             umma_commit(&bars->empty[s]);
                         }
-                    umma_commit(&bars->p_free[pb]);
-                }
-            }
-            umma_commit(&bars->o_full);
-        }
-    } else {
-        const int q = warp & 3;
-        const int r_local = q * 32 + lane;
-        const int row = m_tile * BM + r_local;
-        const bool row_ok = row < P.B;
-        float lse_row = 0.f;      // two-pass: the row's log-sum-exp; one-pass: the fixed shift
-        if (row_ok) {
-            if (onepass) {
-                lse_row = fmaxf(0.f, P.bound[row] - kOnepassShift);
-            } else if (P.lse) {
-                lse_row = P.lse[row];
-            } else {   // merge the forward partials here instead of in a separate launch
-                const float* pm = P.part_m + (size_t)row * P.lse_splits;
-                const float* pl = P.part_l + (size_t)row * P.lse_splits;
-                float M = -INFINITY;
-                for (int sp = 0; sp < P.lse_splits; ++sp) M = fmaxf(M, pm[sp]);
-                float l = 0.f;
-                for (int sp = 0; sp < P.lse_splits; ++sp) l += pl[sp] * expf(pm[sp] - M);
-                lse_row = M + logf(l);
-                if (chunk == 0 && split == 0) P.lse_out[row] = lse_row;
-            }
-        }
-        const float lse2 = lse_row * kLog2e;
-        const uint32_t lane_base = uint32_t(q * 32) << 16;
-        float lsum = 0.f;
-        for (int ti = 0; ti < T; ++ti) {
-            const int pb = ti & 1;
-            mbar_wait(&bars->s_full, ti & 1);
-            tc_fence_after();
-            float v[4][32];
+                        umma_commit(&bars->s_full);
+                    }
+                    if (ti >= 1) {         // G2(ti-1): O += P E_t
+                        const int tj = ti - 1, g = sweep * T + tj, pb = g & 1;
+                        mbar_wait(&bars->p_full[pb], (g >> 1) & 1);
+                        tc_fence_after();
+                        const uint32_t p0 = smem_u32(pbuf + pb * G_PBYTES);
+                        for (int ih = 0; ih < 2; ++ih)
+                            for (int gq = 0; gq < NG; ++gq, ++it) {
+                                const int ncols = min(256, DC - gq * 256);
+                                const uint32_t idesc2 = make_idesc(BM, ncols, 0, 1);
+                                const int s = it % G_STAGES;
+                                mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
+                                tc_fence_after();
+                                const uint32_t b0 = smem_u32(smem + s * G_SLOT);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(tmem_S + lane_base + c * 32, v[c]);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->s_free);
-            mbar_wait(&bars->p_free[pb], ((ti >> 1) & 1) ^ 1);
-            uint8_t* prow = pbuf + pb * G_PBYTES + r_local * 128;
-            auto store = [&](int item, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {   // item: local index 0..127
-                const int atom = item >> 6, chunk16 = (item & 63) >> 3;
-                uint8_t* dst = prow + atom * 16384 + ((chunk16 ^ (r_local & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, w2, w3);
-            };
-            const int n_valid = P.N - (t0 + ti) * G_BN;
-            if (n_valid >= G_BN) lsum += softmax_tile<false>(v, lse2, G_BN, store);
-            else lsum += softmax_tile<true>(v, lse2, n_valid, store);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->p_full[pb]);
+                                for (int kk = 0; kk < 4; ++kk)      // K = 16 items per MMA
+                                    umma_ss(tmem_O + gq * 256, make_desc(p0 + ih * 16384 + kk * 32, 16, 1024),
+                                            make_desc(b0 + kk * 2048, 8192, 1024), idesc2, (tj | ih | kk) != 0);
+                                umma_commit(&bars->empty[s]);
+                            }
+                        umma_commit(&bars->p_free[pb]);
+                    }
+                }
+                umma_commit(&bars->o_full);
+            }
+        } else {
+            const float lse2 = lse_row * kLog2e;
+            lsum = 0.f;
+            for (int ti = 0; ti < T; ++ti) {
+                const int g = sweep * T + ti, pb = g & 1;
+                mbar_wait(&bars->s_full, g & 1);
+                tc_fence_after();
+                float v[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld32(tmem_S + lane_base + c * 32, v[c]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->s_free);
+                mbar_wait(&bars->p_free[pb], ((g >> 1) & 1) ^ 1);
+                uint8_t* prow = pbuf + pb * G_PBYTES + r_local * 128;
+                auto store = [&](int item, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {   // item: local index 0..127
+                    const int atom = item >> 6, chunk16 = (item & 63) >> 3;
+                    uint8_t* dst = prow + atom * 16384 + ((chunk16 ^ (r_local & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, w2, w3);
+                };
+                const int n_valid = P.N - (t0 + ti) * G_BN;
+                if (n_valid >= G_BN) lsum += softmax_tile<false>(v, lse2, G_BN, store);
+                else lsum += softmax_tile<true>(v, lse2, n_valid, store);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->p_full[pb]);
+            }
+            mbar_wait(&bars->o_full, sweep & 1);      // every MMA of the sweep has completed
+            tc_fence_after();
         }
-        if (onepass && row_ok && chunk == 0) P.l_part[(size_t)split * P.B + row] = lsum;
+        __syncwarp();
+        if (!onepass) break;
+        const bool over = warp >= 2 && lsum > kOnepassOverflow;      // inf included; NaN is not (it propagates, as in the reference)
+        if (!__syncthreads_or(over)) break;
+        if (over) lse_row += kOnepassRetry;
+    }
+    if (warp >= 2) {
         // ---- O (TMEM) -> global partial ---------------------------------------------------------------------
-        mbar_wait(&bars->o_full, 0);
-        tc_fence_after();
+        if (onepass && row_ok && chunk == 0) {
+            P.c_part[(size_t)split * P.B + row] = lse_row;
+            P.l_part[(size_t)split * P.B + row] = lsum;
+        }
         float* orow = P.Opart + ((size_t)split * P.B + row) * P.ldo + dc0;
         for (int c = 0; c < DC / 32; ++c) {
             float v[32];
@@ -595,6 +618,8 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
 // G2 lags two tiles behind G1 so that a tile's softmax (and the DSMEM copy) hides behind the two G2s in between.
 // P buffer b = tile & 1 is always written by CTA b: p_full[b] collects that CTA's four softmax warps (local or remote
 // arrives); p_free[b] lives in CTA b and collects the G2 completion of both CTAs (tcgen05.commit to a cluster address).
+// Barrier phases count the uses of a buffer across (possibly repeated) sweeps: CTA/buffer b sees nb(b) = #{tile : tile & 1 == b}
+// uses per sweep.
 __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_constant__ CUtensorMap tmU,
                                                                  const __grid_constant__ CUtensorMap tmE, GradParams P) {
     pdl_launch_dependents();
@@ -632,152 +657,165 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
     pdl_wait();
     const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
     auto own = [&](int ti) { return (uint32_t)(ti & 1) == rank; };
-    const bool onepass = P.gate == 1;
-    const bool active = P.gate == 0 || tile_flagged(P.bound, m_tile, P.B) == (P.gate == 2);   // same decision in both CTAs of the pair
+    auto uses = [&](int b) { return (T + 1 - b) >> 1; };              // tiles of parity b per sweep
+    const bool onepass = P.shift != nullptr;
 
-    if (!active) {
-        // this user tile belongs to the other mode's launch
-    } else if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            auto acquire = [&](uint32_t bytes) {
-                const int s = it % G_STAGES;
-                mbar_wait(&bars->empty[s], ((it / G_STAGES) & 1) ^ 1);
-                mbar_expect_tx(&bars->full[s], bytes);
-                ++it;
-                return s;
-            };
-            for (int ti = 0; ti < T + 2; ++ti) {
-                if (ti < T && own(ti)) {          // G1 operands of my tile ti
-                    const int item0 = (t0 + ti) * G_BN;
-                    for (int kb = 0; kb < KB; ++kb) {
-                        const int s = acquire(G_SLOT);
-                        uint8_t* slot = smem + s * G_SLOT;
-                        tma_load_2d(slot, &tmU, kb * BK, m_tile * BM, &bars->full[s]);
-                        tma_load_2d(slot + 16384, &tmE, kb * BK, item0, &bars->full[s]);
-                        tma_load_2d(slot + 16384 + 8192, &tmE, kb * BK, item0 + 64, &bars->full[s]);
-                    }
-                }
-                if (ti >= 2) {                    // G2 operands of tile ti-2 (every tile, my column chunk)
-                    const int item0 = (t0 + ti - 2) * G_BN;
-                    for (int ih = 0; ih < 2; ++ih)
-                        for (int g = 0; g < NG; ++g) {
-                            const int nb = min(4, (DC - g * 256) / 64);
-                            const int s = acquire(nb * 8192);
+    const int q = warp & 3;
+    const int r_local = q * 32 + lane;
+    const int row = m_tile * BM + r_local;
+    const bool row_ok = warp >= 2 && row < P.B;
+    const uint32_t lane_base = uint32_t(q * 32) << 16;
+    float lse_row = 0.f;      // two-pass: the row's log-sum-exp; one-pass: the shift
+    if (row_ok) {
+        if (onepass) lse_row = P.shift[row];
+        else if (P.lse) lse_row = P.lse[row];
+        else {
+            lse_row = merged_lse(P.part_m, P.part_l, P.lse_splits, row);
+            if (chunk == 0 && split == 0) P.lse_out[row] = lse_row;
+        }
+    }
+    float lsum = 0.f;
+    int it = 0;
+    const int pb_mine = (int)rank;                                  // the P buffer this CTA writes
+    const uint32_t pfull_local = smem_u32(&bars->p_full[pb_mine]);
+    const uint32_t pfull_peer = map_to_cta(pfull_local, peer);
+    const uint32_t prow_local = smem_u32(pbuf + pb_mine * G_PBYTES + r_local * 128);
+    const uint32_t prow_peer = map_to_cta(prow_local, peer);
+
+    for (int sweep = 0;; ++sweep) {
+        if (warp == 0) {
+            if (lane == 0) {
+                auto acquire = [&](uint32_t bytes) {
+                    const int s = it % G_STAGES;
+                    mbar_wait(&bars->empty[s], ((it / G_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&bars->full[s], bytes);
+                    ++it;
+                    return s;
+                };
+                for (int ti = 0; ti < T + 2; ++ti) {
+                    if (ti < T && own(ti)) {          // G1 operands of my tile ti
+                        const int item0 = (t0 + ti) * G_BN;
+                        for (int kb = 0; kb < KB; ++kb) {
+                            const int s = acquire(G_SLOT);
                             uint8_t* slot = smem + s * G_SLOT;
-                            for (int j = 0; j < nb; ++j)
-                                tma_load_2d(slot + j * 8192, &tmE, dc0 + g * 256 + j * 64, item0 + ih * 64, &bars->full[s]);
+                            tma_load_2d(slot, &tmU, kb * BK, m_tile * BM, &bars->full[s]);
+                            tma_load_2d(slot + 16384, &tmE, kb * BK, item0, &bars->full[s]);
+                            tma_load_2d(slot + 16384 + 8192, &tmE, kb * BK, item0 + 64, &bars->full[s]);
                         }
+                    }
+                    if (ti >= 2) {                    // G2 operands of tile ti-2 (every tile, my column chunk)
+                        const int item0 = (t0 + ti - 2) * G_BN;
+                        for (int ih = 0; ih < 2; ++ih)
+                            for (int g = 0; g < NG; ++g) {
+                                const int nb = min(4, (DC - g * 256) / 64);
+                                const int s = acquire(nb * 8192);
+                                uint8_t* slot = smem + s * G_SLOT;
+                                for (int j = 0; j < nb; ++j)
+                                    tma_load_2d(slot + j * 8192, &tmE, dc0 + g * 256 + j * 64, item0 + ih * 64, &bars->full[s]);
+                            }
+                    }
                 }
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = make_idesc(BM, G_BN, 0, 0);
-            int it = 0;
-            for (int ti = 0; ti < T + 2; ++ti) {
-                if (ti < T && own(ti)) {          // G1(ti): S = U E_t^T
-                    const int k = ti >> 1;        // my k-th own tile
-                    mbar_wait(&bars->s_free, (k & 1) ^ 1);
-                    tc_fence_after();
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        const int s = it % G_STAGES;
-                        mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc1 = make_idesc(BM, G_BN, 0, 0);
+                for (int ti = 0; ti < T + 2; ++ti) {
+                    if (ti < T && own(ti)) {          // G1(ti): S = U E_t^T
+                        const int k = sweep * uses((int)rank) + (ti >> 1);        // my k-th own tile overall
+                        mbar_wait(&bars->s_free, (k & 1) ^ 1);
                         tc_fence_after();
-                        const uint32_t a0 = smem_u32(smem + s * G_SLOT), b0 = a0 + 16384;
-#pragma unroll
-                        for (int kk = 0; kk < BK / 16; ++kk)
-                            umma_ss(tmem_S, make_desc(a0 + kk * 32, 16, 1024), make_desc(b0 + kk * 32, 16, 1024), idesc1, (kb | kk) != 0);
-                        umma_commit(&bars->empty[s]);
-                    }
-                    umma_commit(&bars->s_full);
-                }
-                if (ti >= 2) {                    // G2(ti-2): O += P E_t
-                    const int tj = ti - 2, pb = tj & 1;
-                    mbar_wait_cluster(&bars->p_full[pb], (tj >> 1) & 1);      // P may have been written by the peer CTA
-                    fence_proxy_async_all();
-                    tc_fence_after();
-                    const uint32_t p0 = smem_u32(pbuf + pb * G_PBYTES);
-                    for (int ih = 0; ih < 2; ++ih)
-                        for (int g = 0; g < NG; ++g, ++it) {
-                            const int ncols = min(256, DC - g * 256);
-                            const uint32_t idesc2 = make_idesc(BM, ncols, 0, 1);
+                        for (int kb = 0; kb < KB; ++kb, ++it) {
                             const int s = it % G_STAGES;
                             mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
                             tc_fence_after();
-                            const uint32_t b0 = smem_u32(smem + s * G_SLOT);
+                            const uint32_t a0 = smem_u32(smem + s * G_SLOT), b0 = a0 + 16384;
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_ss(tmem_O + g * 256, make_desc(p0 + ih * 16384 + kk * 32, 16, 1024),
-                                        make_desc(b0 + kk * 2048, 8192, 1024), idesc2, (tj | ih | kk) != 0);
+                            for (int kk = 0; kk < BK / 16; ++kk)
+                                umma_ss(tmem_S, make_desc(a0 + kk * 32, 16, 1024), make_desc(b0 + kk * 32, 16, 1024), idesc1, (kb | kk) != 0);
                             umma_commit(&bars->empty[s]);
                         }
-                    // buffer pb may be rewritten once BOTH CTAs are done with it: its owner (CTA pb) collects both commits
-                    umma_commit_cluster(map_to_cta(smem_u32(&bars->p_free[pb]), (uint32_t)pb));
+                        umma_commit(&bars->s_full);
+                    }
+                    if (ti >= 2) {                    // G2(ti-2): O += P E_t
+                        const int tj = ti - 2, pb = tj & 1;
+                        const int u = sweep * uses(pb) + (tj >> 1);               // use count of buffer pb
+                        mbar_wait_cluster(&bars->p_full[pb], u & 1);              // P may have been written by the peer CTA
+                        fence_proxy_async_all();
+                        tc_fence_after();
+                        const uint32_t p0 = smem_u32(pbuf + pb * G_PBYTES);
+                        for (int ih = 0; ih < 2; ++ih)
+                            for (int g = 0; g < NG; ++g, ++it) {
+                                const int ncols = min(256, DC - g * 256);
+                                const uint32_t idesc2 = make_idesc(BM, ncols, 0, 1);
+                                const int s = it % G_STAGES;
+                                mbar_wait(&bars->full[s], (it / G_STAGES) & 1);
+                                tc_fence_after();
+                                const uint32_t b0 = smem_u32(smem + s * G_SLOT);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_ss(tmem_O + g * 256, make_desc(p0 + ih * 16384 + kk * 32, 16, 1024),
+                                            make_desc(b0 + kk * 2048, 8192, 1024), idesc2, (tj | ih | kk) != 0);
+                                umma_commit(&bars->empty[s]);
+                            }
+                        // buffer pb may be rewritten once BOTH CTAs are done with it: its owner (CTA pb) collects both commits
+                        umma_commit_cluster(map_to_cta(smem_u32(&bars->p_free[pb]), (uint32_t)pb));
+                    }
+                }
+                umma_commit(&bars->o_full);
+            }
+        } else {
+            const float lse2 = lse_row * kLog2e;
+            lsum = 0.f;
+            for (int ti = (int)rank; ti < T; ti += 2) {                 // my tiles only
+                const int k = sweep * uses((int)rank) + (ti >> 1);
+                mbar_wait(&bars->s_full, k & 1);
+                tc_fence_after();
+                float v[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld32(tmem_S + lane_base + c * 32, v[c]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->s_free);
+                mbar_wait_cluster(&bars->p_free[pb_mine], (k & 1) ^ 1);      // both CTAs finished G2 of my previous tile
+                auto store = [&](int item, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+                    const uint32_t off = (uint32_t)((item >> 6) * 16384 + ((((item & 63) >> 3) ^ (r_local & 7)) << 4));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_local + off), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+                    st_cluster_v4(prow_peer + off, w0, w1, w2, w3);
+                };
+                const int n_valid = P.N - (t0 + ti) * G_BN;
+                if (n_valid >= G_BN) lsum += softmax_tile<false>(v, lse2, G_BN, store);
+                else lsum += softmax_tile<true>(v, lse2, n_valid, store);
+                fence_proxy_async_all();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&bars->p_full[pb_mine]);
+                    mbar_arrive_cluster(pfull_peer);
                 }
             }
-            umma_commit(&bars->o_full);
-        }
-    } else {
-        const int q = warp & 3;
-        const int r_local = q * 32 + lane;
-        const int row = m_tile * BM + r_local;
-        const bool row_ok = row < P.B;
-        float lse_row = 0.f;      // two-pass: the row's log-sum-exp; one-pass: the fixed shift
-        if (row_ok) {
-            if (onepass) {
-                lse_row = fmaxf(0.f, P.bound[row] - kOnepassShift);
-            } else if (P.lse) {
-                lse_row = P.lse[row];
-            } else {
-                const float* pm = P.part_m + (size_t)row * P.lse_splits;
-                const float* pl = P.part_l + (size_t)row * P.lse_splits;
-                float M = -INFINITY;
-                for (int sp = 0; sp < P.lse_splits; ++sp) M = fmaxf(M, pm[sp]);
-                float l = 0.f;
-                for (int sp = 0; sp < P.lse_splits; ++sp) l += pl[sp] * expf(pm[sp] - M);
-                lse_row = M + logf(l);
-                if (chunk == 0 && split == 0) P.lse_out[row] = lse_row;
-            }
-        }
-        const float lse2 = lse_row * kLog2e;
-        const uint32_t lane_base = uint32_t(q * 32) << 16;
-        const int pb = (int)rank;                                   // the buffer this CTA writes
-        const uint32_t pfull_local = smem_u32(&bars->p_full[pb]);
-        const uint32_t pfull_peer = map_to_cta(pfull_local, peer);
-        const uint32_t prow_local = smem_u32(pbuf + pb * G_PBYTES + r_local * 128);
-        const uint32_t prow_peer = map_to_cta(prow_local, peer);
-        float lsum = 0.f;
-        for (int ti = (int)rank, k = 0; ti < T; ti += 2, ++k) {     // my tiles only
-            mbar_wait(&bars->s_full, k & 1);
+            mbar_wait(&bars->o_full, sweep & 1);      // every MMA of this CTA's sweep has completed
             tc_fence_after();
-            float v[4][32];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(tmem_S + lane_base + c * 32, v[c]);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->s_free);
-            mbar_wait_cluster(&bars->p_free[pb], (k & 1) ^ 1);      // both CTAs finished G2 of my previous tile
-            auto store = [&](int item, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-                const uint32_t off = (uint32_t)((item >> 6) * 16384 + ((((item & 63) >> 3) ^ (r_local & 7)) << 4));
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_local + off), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-                st_cluster_v4(prow_peer + off, w0, w1, w2, w3);
-            };
-            const int n_valid = P.N - (t0 + ti) * G_BN;
-            if (n_valid >= G_BN) lsum += softmax_tile<false>(v, lse2, G_BN, store);
-            else lsum += softmax_tile<true>(v, lse2, n_valid, store);
-            fence_proxy_async_all();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bars->p_full[pb]);
-                mbar_arrive_cluster(pfull_peer);
-            }
         }
-        if (onepass && row_ok) P.l_part[((size_t)split * 2 + rank) * P.B + row] = lsum;     // each CTA of the pair: its own tiles
+        __syncwarp();
+        if (!onepass) break;
+        // a row overflowed in either CTA (each saw only its own tiles) -> both repeat the sweep with the same larger shift
+        if (warp >= 2) {
+            const uint8_t f = lsum > kOnepassOverflow ? 1 : 0;
+            bars->retry[rank][r_local] = f;
+            const uint32_t remote = map_to_cta(smem_u32(&bars->retry[rank][r_local]), peer);
+            asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(remote), "r"((uint32_t)f) : "memory");
+        }
+        cluster_sync_all();
+        const bool over = warp >= 2 && (bars->retry[0][r_local] | bars->retry[1][r_local]) != 0;
+        if (!__syncthreads_or(over)) break;
+        if (over) lse_row += kOnepassRetry;
+    }
+    if (warp >= 2) {
         // ---- O (TMEM) -> global partial ---------------------------------------------------------------------
-        mbar_wait(&bars->o_full, 0);
-        tc_fence_after();
+        if (onepass && row_ok) {
+            if (rank == 0) P.c_part[(size_t)split * P.B + row] = lse_row;
+            P.l_part[((size_t)split * 2 + rank) * P.B + row] = lsum;        // each CTA of the pair: its own tiles
+        }
         float* orow = P.Opart + ((size_t)split * P.B + row) * P.ldo + dc0;
         for (int c = 0; c < DC / 32; ++c) {
             float v[32];
@@ -801,7 +839,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
     }
 }
 
-constexpr size_t kGradSmem = G_STAGES * G_SLOT + 2 * G_PBYTES + 256 + 1024;
+constexpr size_t kGradSmem = G_STAGES * G_SLOT + 2 * G_PBYTES + 512 + 1024;
 
 // Item splits per (user tile, column chunk): one CTA per SM in a single wave when each CTA would otherwise get only a
 // few tiles (the prologue -- barrier init, TMEM alloc, first TMA -- costs about one tile), two waves for long CTAs.
@@ -885,7 +923,7 @@ size_t hvae_tc_n_splits(int B, int N) { return (size_t)pick_splits(ceil_div(B, B
 size_t hvae_tc_topk_splits(int B, int N) { return (size_t)pick_topk_splits(ceil_div(B, BM), ceil_div(N, BN)); }
 
 static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* workspace, int* n_splits,
-                            cudaStream_t stream, const float* bound = nullptr, int gate = 0) {
+                            cudaStream_t stream) {
     CUtensorMap tmU, tmE;
     if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
     if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, BN)) return rc;
@@ -896,7 +934,6 @@ static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int ld
     P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
     P.part_m = workspace;
     P.part_l = workspace + (size_t)B * P.n_splits;
-    P.bound = bound; P.gate = gate;
     static bool attr_set = false;
     if (!attr_set) {
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
@@ -915,7 +952,7 @@ static bool grad_is_pair(int d) {
 
 static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, const float* part_m,
                        const float* part_l, int lse_splits, float* lse_out, float* Opart, int ldo, cudaStream_t stream,
-                       const float* bound = nullptr, int gate = 0, float* l_part = nullptr) {
+                       const float* shift = nullptr, float* c_part = nullptr, float* l_part = nullptr) {
     HVAE_REQUIRE(ldo % 4 == 0 && ldo >= d, "tc_score_grad: bad ldo=%d for d=%d", ldo, d);
     CUtensorMap tmU, tmE;
     if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
@@ -924,7 +961,7 @@ static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, in
     GradParams P{};
     P.B = B; P.N = N; P.d = d; P.lse = lse; P.part_m = part_m; P.part_l = part_l; P.lse_splits = lse_splits; P.lse_out = lse_out;
     P.Opart = Opart; P.ldo = ldo;
-    P.bound = bound; P.gate = gate; P.l_part = l_part;
+    P.shift = shift; P.c_part = c_part; P.l_part = l_part;
     P.n_splits = pick_grad_splits(m_tiles, n_chunks, n_tiles);
     P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
     static bool attr_set = false;
@@ -1003,43 +1040,34 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
 }
 
 
-int hvae_cast_bf16_bound(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, float scale, float* bound,
-                         void* stream) {
+int hvae_cast_bf16_probe(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, const void* E, int lde, int N,
+                         float* shift, void* stream) {
     if (rows == 0) return 0;
-    launch_pdl(cast_bf16_bound_kernel, ceil_div(rows, 8), 256, 0, (cudaStream_t)stream, src, rows, cols, ld_src, (__nv_bfloat16*)dst, ld_dst, scale,
-               bound);
-    HVAE_LAUNCH_CHECK("cast_bf16_bound");
+    launch_pdl(cast_bf16_probe_kernel, ceil_div(rows, 8), 256, 0, (cudaStream_t)stream, src, rows, cols, ld_src, (__nv_bfloat16*)dst, ld_dst,
+               (const __nv_bfloat16*)E, lde, min(N, kMaxProbe), shift);
+    HVAE_LAUNCH_CHECK("cast_bf16_probe");
     return 0;
 }
 
-// floats: row-sum partials of the one-pass kernel + the (max, sum-exp) partials of the gated fallback
-size_t hvae_tc_onepass_workspace_floats(int B, int N, int d) {
-    const size_t gs = hvae_tc_grad_splits(B, N, d);
-    return (size_t)B * (2 * gs + 2 * hvae_tc_n_splits(B, N));
-}
+// 1 or 2 numerator sums per (split, row): the pair kernel's two CTAs each report the tiles they owned
+size_t hvae_tc_onepass_subparts(int d) { return grad_is_pair(d) ? 2 : 1; }
 
 // Forward and backward through the scores in ONE sweep over the items (4 B N d executed flops instead of the 6 B N d of
-// hvae_tc_score_lse_grad): the backward kernel takes the softmax numerators against a fixed shift derived from `bound`
-// (hvae_cast_bf16_bound) and also returns their row sums.  Opart then holds UNNORMALISED sums: O = inv_l * sum_p Opart[p].
-// User tiles whose bound is outside the safe range run the two-pass kernels instead (same launch sequence every call, the
-// kernels of the mode a tile does not use exit at once), inv_l = 1 for their rows.
-int hvae_tc_score_onepass(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* bound, float* lse,
-                          float* inv_l, float* workspace, float* Opart, int ldo, void* stream) {
+// hvae_tc_score_lse_grad): the backward kernel takes the softmax numerators against the fixed per-row shift (a lower bound of
+// the row's largest score, hvae_cast_bf16_probe) and also returns their row sums.  Opart then holds UNNORMALISED sums;
+// hvae_du_finalize combines them with (c_part, l_part), hvae_tc_onepass_lse gives the log-sum-exp.
+int hvae_tc_score_onepass(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* shift, float* c_part,
+                          float* l_part, float* Opart, int ldo, void* stream) {
     if (B == 0) return 0;
     HVAE_REQUIRE(N > 0 && d > 0, "tc_score_onepass: empty catalogue");
-    const size_t gs = hvae_tc_grad_splits(B, N, d);
-    const int n_lparts = (int)gs * (grad_is_pair(d) ? 2 : 1);
-    float* l_part = workspace;
-    float* lse_ws = workspace + 2 * gs * (size_t)B;
-    if (int rc = launch_grad(U, ldu, B, E, lde, N, d, nullptr, nullptr, nullptr, 0, nullptr, Opart, ldo, (cudaStream_t)stream, bound, 1, l_part))
-        return rc;
-    int ns = 0;
-    if (int rc = launch_stats_lse(U, ldu, B, E, lde, N, d, lse_ws, &ns, (cudaStream_t)stream, bound, 2)) return rc;
-    if (int rc = launch_grad(U, ldu, B, E, lde, N, d, nullptr, lse_ws, lse_ws + (size_t)B * ns, ns, lse, Opart, ldo, (cudaStream_t)stream, bound, 2,
-                             nullptr))
-        return rc;
-    launch_pdl(onepass_finalize_kernel, ceil_div(B, 128), 128, 0, (cudaStream_t)stream, bound, (const float*)l_part, n_lparts, B, lse, inv_l);
-    HVAE_LAUNCH_CHECK("tc_score_onepass finalize");
+    HVAE_REQUIRE(shift && c_part && l_part, "tc_score_onepass: shift / c_part / l_part are required");
+    return launch_grad(U, ldu, B, E, lde, N, d, nullptr, nullptr, nullptr, 0, nullptr, Opart, ldo, (cudaStream_t)stream, shift, c_part, l_part);
+}
+
+int hvae_tc_onepass_lse(const float* c_part, const float* l_part, int n_parts, int n_sub, int B, float* lse, void* stream) {
+    if (B == 0) return 0;
+    launch_pdl(onepass_lse_kernel, ceil_div(B, 128), 128, 0, (cudaStream_t)stream, c_part, l_part, n_parts, n_sub, B, lse);
+    HVAE_LAUNCH_CHECK("tc_onepass_lse");
     return 0;
 }
 

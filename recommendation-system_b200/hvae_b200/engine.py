@@ -236,7 +236,6 @@ class Engine:
         self.slot_of_item = None
         self.dist = None  # set by hvae_b200.dist for data-parallel training
         self._E_bf16 = None
-        self._E_max_norm = None
         self.two_pass = os.environ.get("HVAE_TWO_PASS", "0") == "1"   # bf16 training: forward-LSE + backward launches instead of the one-pass kernel
         self.prof = None  # dict name -> [(start, stop) events] when profiling spans are enabled
         self.concurrent, self._side, self._forked = False, [], set()
@@ -280,22 +279,8 @@ class Engine:
             self.lib.cast_bf16(p(self.E), N, d, d, p(self._E_bf16), r8(d), self.stream)
         return self._E_bf16
 
-    @property
-    def E_max_norm(self) -> float:
-        """max_i ||E_i||_2 of the bf16 item matrix: with ||u_b|| it bounds every score of a user (one-pass scoring kernel)."""
-        if self._E_max_norm is None:
-            Eb = self.E_bf16
-            N = Eb.shape[0]
-            norms = torch.empty(N, dtype=torch.float32, device=self.dev)
-            scratch = torch.empty_like(Eb)
-            src = Eb.float()
-            self.lib.cast_bf16_bound(p(src), N, Eb.shape[1], Eb.shape[1], p(scratch), Eb.shape[1], 1.0, p(norms), self.stream)
-            self._E_max_norm = float(norms.max().item())
-        return self._E_max_norm
-
     def invalidate_embeddings(self):
         self._E_bf16 = None
-        self._E_max_norm = None
 
     # -- helpers -----------------------------------------------------------------------------------------
     @property
@@ -470,9 +455,9 @@ class Engine:
             is_bf16 = 0 if self.precision == "fp32" else 1
             Eg, lde = (self.E, d) if not is_bf16 else (self.E_bf16, r8(d))
             n_parts = O.shape[0] if O.dim() == 3 else 1
-            oscale, oscale2 = oscale if isinstance(oscale, tuple) else (oscale, None)
-            lib.du_finalize(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(O), ldd, n_parts, p(oscale), p(oscale2),
-                            p(Eg), lde, d, is_bf16, self.state_ptr("inv_bg"), p(dU), ldd, st)
+            oscale, c_part, l_part, n_sub = oscale if isinstance(oscale, tuple) else (oscale, None, None, 0)
+            lib.du_finalize(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(O), ldd, n_parts, p(oscale), p(c_part),
+                            p(l_part), n_sub, p(Eg), lde, d, is_bf16, self.state_ptr("inv_bg"), p(dU), ldd, st)
         if lay.identity_proj:
             dz = dU
         else:

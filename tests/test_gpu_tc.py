@@ -124,74 +124,79 @@ def test_tc_grad_matches_torch(dev, B, N, d):
 
 
 def _onepass(lib, dev, U, E, st):
-    """-> (lse, O normalised [B, d], bound) of hvae_tc_score_onepass on the bf16-rounded operands."""
+    """hvae_tc_score_onepass on the bf16-rounded operands -> (lse, O [B, d] combined as hvae_du_finalize does, c_part, S, E)."""
     B, d = U.shape
     N = E.shape[0]
     Eb, lde = _cast(lib, E.contiguous(), dev)
-    emax = float(Eb.float().norm(dim=1).max())
     ldu = _r8(d)
     Ub = torch.empty(B, ldu, dtype=torch.bfloat16, device=dev)
-    bound = torch.empty(B, device=dev)
-    lib.cast_bf16_bound(U.contiguous().data_ptr(), B, d, d, Ub.data_ptr(), ldu, emax, bound.data_ptr(), st)
+    shift = torch.empty(B, device=dev)
+    lib.cast_bf16_probe(U.contiguous().data_ptr(), B, d, d, Ub.data_ptr(), ldu, Eb.data_ptr(), lde, N, shift.data_ptr(), st)
     assert torch.equal(Ub[:, :d], U.to(torch.bfloat16)) and torch.all(Ub[:, d:] == 0)
     S = Ub[:, :d].float().double() @ Eb[:, :d].float().double().t()
-    assert bool((bound.double() >= S.abs().max(dim=1).values).all())          # a true upper bound of every score
+    np.testing.assert_allclose(shift.cpu().numpy(), S[:, :min(N, 8)].max(dim=1).values.cpu().numpy(), rtol=1e-5, atol=1e-5)
     gs = int(lib.tc_grad_splits(B, N, d))
+    n_sub = int(lib.tc_onepass_subparts(d))
     ldo = (d + 3) // 4 * 4
     Op = torch.full((gs, B, ldo), float("nan"), device=dev)
+    c_part = torch.full((gs, B), float("nan"), device=dev)
+    l_part = torch.full((gs, n_sub, B), float("nan"), device=dev)
     lse = torch.full((B,), float("nan"), device=dev)
-    inv_l = torch.full((B,), float("nan"), device=dev)
-    ws = torch.empty(int(lib.tc_onepass_workspace_floats(B, N, d)), device=dev)
-    lib.tc_score_onepass(Ub.data_ptr(), ldu, B, Eb.data_ptr(), lde, N, d, bound.data_ptr(), lse.data_ptr(), inv_l.data_ptr(), ws.data_ptr(),
+    lib.tc_score_onepass(Ub.data_ptr(), ldu, B, Eb.data_ptr(), lde, N, d, shift.data_ptr(), c_part.data_ptr(), l_part.data_ptr(),
                          Op.data_ptr(), ldo, st)
-    O = (Op.double().sum(0) * inv_l.double()[:, None])[:, :d]
-    return lse, O, bound, S, Eb[:, :d].float().double()
+    lib.tc_onepass_lse(c_part.data_ptr(), l_part.data_ptr(), gs, n_sub, B, lse.data_ptr(), st)
+    # the combination hvae_du_finalize applies: O = sum_p e^{c_p - M} O_p / sum_p e^{c_p - M} l_p   (checked through the C ABI
+    # itself with an empty interaction matrix and oscale = 1, 1/Bg = 1)
+    ip = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+    ix = torch.zeros(1, dtype=torch.int32, device=dev)
+    one = torch.ones(B, device=dev)
+    inv_bg = torch.ones(1, device=dev)
+    dU = torch.empty(B, ldo, device=dev)
+    lib.du_finalize(ip.data_ptr(), ix.data_ptr(), None, None, B, Op.data_ptr(), ldo, gs, one.data_ptr(), c_part.data_ptr(), l_part.data_ptr(),
+                    n_sub, Eb.data_ptr(), lde, d, 1, inv_bg.data_ptr(), dU.data_ptr(), ldo, st)
+    return lse, dU[:, :d].double(), c_part, shift, S, Eb[:, :d].float().double()
 
 
 @pytest.mark.parametrize("B,N,d", [(512, 12101, 384), (128, 256, 64), (77, 1000, 64), (300, 5000, 768), (130, 890, 384), (64, 300, 24),
-                                   (1, 513, 200), (256, 3000, 448), (200, 1100, 1000)])
+                                   (1, 513, 200), (256, 3000, 448), (200, 1100, 1000), (5, 3, 16)])
 def test_tc_onepass_matches_torch(dev, B, N, d):
     """Forward + backward through the scores in one sweep: lse and O = softmax(S) E from numerators against a fixed shift."""
     from hvae_b200 import _cabi
     lib = _cabi.lib()
     st = torch.cuda.current_stream().cuda_stream
     U, E = _operands(B, N, d, dev, seed=2)
-    lse, O, bound, S, Ed = _onepass(lib, dev, U, E, st)
-    assert float(bound.max()) < 55.0                                          # every tile on the one-pass kernel
+    lse, O, c_part, shift, S, Ed = _onepass(lib, dev, U, E, st)
+    assert torch.equal(c_part, shift[None, :].expand_as(c_part))               # no sweep had to be repeated
     np.testing.assert_allclose(lse.cpu().numpy(), torch.logsumexp(S, dim=1).cpu().numpy(), rtol=2e-6, atol=2e-5)
-    Pm = torch.softmax(S, dim=1)
-    ref = Pm @ Ed
+    ref = torch.softmax(S, dim=1) @ Ed
     scale = float(ref.abs().max())
     assert torch.isfinite(O).all()
     assert float((O - ref).abs().max()) < 1e-2 * scale + 1e-6                 # bf16 rounding of the numerators
 
 
-def test_tc_onepass_shift_and_fallback(dev):
-    """Rows with large norms: bound in (40, 55] exercises a non-zero shift, bound > 55 sends that user tile (and only it) to
-    the two-pass kernels inside the same call; peaked and flat rows in one batch."""
+def test_tc_onepass_overflow_retry(dev):
+    """Rows whose largest score lies far above the probe's: the sweep overflows and is repeated with a larger shift -- by the
+    splits that saw the overflow only, so the per-split shifts differ and the combination has to weight them; peaked, flat
+    and all-zero rows in the same batch."""
     from hvae_b200 import _cabi
     lib = _cabi.lib()
     st = torch.cuda.current_stream().cuda_stream
-    for d, N in ((384, 3001), (768, 2500)):
+    for d, N in ((384, 3001), (768, 2500), (64, 40000)):
         B = 300                                                               # three user tiles
         U, E = _operands(B, N, d, dev, seed=5)
-        U = U / U.norm(dim=1, keepdim=True)
-        norms = torch.full((B,), 6.0, device=dev)
-        norms[3] = 48.0                                                       # tile 0: shifted, still one-pass
-        norms[130] = 300.0                                                    # tile 1: beyond the range -> two-pass fallback
-        norms[131] = 90.0
-        norms[260] = 0.0                                                      # tile 2: an all-zero user vector (uniform softmax)
-        U = U * norms[:, None]
-        U[5] = 45.0 * E[17]                                                   # aligned with an item: a very peaked row
-        lse, O, bound, S, Ed = _onepass(lib, dev, U, E, st)
-        flagged = (bound.view(-1)[:256].view(2, 128) > 55.0).any(dim=1).cpu().tolist()
-        assert flagged == [False, True] and not bool((bound[256:] > 55.0).any())
-        ref_lse = torch.logsumexp(S, dim=1)
-        np.testing.assert_allclose(lse.cpu().numpy(), ref_lse.cpu().numpy(), rtol=3e-6, atol=5e-5)
+        U = U / U.norm(dim=1, keepdim=True) * 6.0
+        U[3] = 48.0 * E[17]                                                   # very peaked, but within the first window
+        U[130] = 150.0 * E[N - 5]                                             # S_max = 150 at the end of the catalogue: two retries
+        U[131] = 100.0 * E[N // 2] - 100.0 * E[0]                             # probe far below the maximum
+        U[7] = 500.0 * E[33]                                                  # many retries
+        U[260] = 0.0                                                          # uniform softmax
+        lse, O, c_part, shift, S, Ed = _onepass(lib, dev, U, E, st)
+        moved = (c_part != shift[None, :]).any(dim=0).cpu()
+        assert bool(moved[130]) and bool(moved[131]) and bool(moved[7]) and not bool(moved[260]) and not bool(moved[200])
+        np.testing.assert_allclose(lse.cpu().numpy(), torch.logsumexp(S, dim=1).cpu().numpy(), rtol=3e-6, atol=5e-5)
         ref = torch.softmax(S, dim=1) @ Ed
         assert torch.isfinite(O).all()
-        err = (O - ref).abs().max(dim=1).values
-        assert float(err.max()) < 1e-2 * float(ref.abs().max()) + 1e-6
+        assert float((O - ref).abs().max()) < 1e-2 * float(ref.abs().max()) + 1e-6
 
 
 def test_gemm_tf32_all_layouts(dev):
