@@ -125,12 +125,11 @@ int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const fl
                          void* stream);
 /* dU = s_b * O_b - (1/Bg) * sum_j x_bj E_idx_j;  O: n_parts partial sums [n_parts][B][ldo];
  * s_b = oscale ? oscale[b]/Bg : 1 (oscale = row sums |x|_b when O holds softmax-weighted sums).
- * O_b = sum_p O[p][b], or, with the unnormalised partials of hvae_tc_score_onepass (c_part != NULL),
- * O_b = sum_p e^{c_p} O[p][b] / sum_p e^{c_p} sum_sub l_part[p][sub][b]. */
+ * O_b = sum_p O[p][b], or sum_p w_part[p][b] O[p][b] for the unnormalised partials of hvae_tc_score_onepass
+ * (w_part [n_parts][B] from hvae_tc_onepass_combine; NULL otherwise). */
 int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
-                     const float* O, int ldo, int n_parts, const float* oscale, const float* c_part, const float* l_part,
-                     int n_sub, const void* E, int lde, int d, int is_bf16, const float* inv_bg, float* dU, int lddu,
-                     void* stream);
+                     const float* O, int ldo, int n_parts, const float* oscale, const float* w_part, const void* E, int lde,
+                     int d, int is_bf16, const float* inv_bg, float* dU, int lddu, void* stream);
 /* Seen-item masking (in place) + top-K of materialised scores under the order (score desc, index desc).  Rows are cut into
  * hvae_mask_topk_chunks(n_rows, N) column chunks; cand_val / cand_idx: scratch [n_rows, chunks * K] (NULL if chunks == 1). */
 size_t hvae_mask_topk_chunks(int n_rows, int N);
@@ -178,18 +177,18 @@ int hvae_tc_score_lse_grad(const void* U, int ldu, int B, const void* E, int lde
                            float* Opart, int ldo, void* stream);
 
 /* Forward + backward through the scores in ONE sweep over the items (what a training step uses; 4BNd executed flops instead
- * of 6BNd): softmax numerators are taken against a per-row shift known before the sweep -- the row's best score among the
- * first 8 items (hvae_cast_bf16_probe = hvae_cast_bf16 + that shift), a lower bound of its largest score, so nothing relevant
- * underflows; a row whose numerators overflow makes its CTA repeat the sweep with shift + 60.
+ * of 6BNd): softmax numerators are taken against a per-row shift that does not depend on the scores (0 to begin with), so no
+ * forward pass has to come first; a row whose numerator sum leaves the range in which fp32/bf16 lose nothing (scores beyond
+ * about +-70) makes its CTA repeat the sweep with the shift moved by 60.
  * Out: Opart [S = hvae_tc_grad_splits(B,N,d)][B][ldo] UNNORMALISED partial sums; c_part [S][B] the shift each split ended up
- * with; l_part [S][n_sub = hvae_tc_onepass_subparts(d)][B] row sums of the numerators.  hvae_du_finalize combines them
- * (O_b = sum_p e^{c_p} Opart[p][b] / sum_p e^{c_p} l_p), hvae_tc_onepass_lse gives lse_b = log sum_p e^{c_p} l_p. */
-int hvae_cast_bf16_probe(const float* src, int rows, int cols, int ld_src, void* dst_bf16, int ld_dst, const void* E, int lde,
-                         int N, float* shift, void* stream);
+ * with; l_part [S][n_sub = hvae_tc_onepass_subparts(d)][B] row sums of the numerators.
+ * hvae_tc_onepass_combine: lse_b = log sum_p e^{c_p} l_p and the weights w_part [S][B] = e^{c_p} / sum_q e^{c_q} l_q that
+ * hvae_du_finalize applies (O_b = sum_p w_part[p][b] Opart[p][b]). */
 size_t hvae_tc_onepass_subparts(int d);
-int hvae_tc_score_onepass(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* shift,
-                          float* c_part, float* l_part, float* Opart, int ldo, void* stream);
-int hvae_tc_onepass_lse(const float* c_part, const float* l_part, int n_parts, int n_sub, int B, float* lse, void* stream);
+int hvae_tc_score_onepass(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* c_part, float* l_part,
+                          float* Opart, int ldo, void* stream);
+int hvae_tc_onepass_combine(const float* c_part, const float* l_part, int n_parts, int n_sub, int B, float* lse,
+                            float* w_part, void* stream);
 
 /* ---- optimiser (train.py:63,88-92; model.py:312-323) --------------------------------------------------- */
 /* advance != 0: a training step (Adam step count, annealing step and the noise counter (+= noise_stride) move on) */

@@ -102,8 +102,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                           const float* __restrict__ values, const int32_t* __restrict__ rows, int B,
                                                           const float* __restrict__ O, int ldo, int n_parts,
-                                                          const float* __restrict__ oscale, const float* __restrict__ c_part,
-                                                          const float* __restrict__ l_part, int n_sub,
+                                                          const float* __restrict__ oscale, const float* __restrict__ w_part,
                                                           const T* __restrict__ E, int lde, int d,
                                                           const float* __restrict__ inv_bg, float* __restrict__ dU, int lddu) {
     pdl_prologue();
@@ -112,36 +111,37 @@ __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restr
     if (t >= B * ld4) return;
     const int b = t / ld4, c = (t - b * ld4) * 4;
     const int u = rows ? rows[b] : b;
-    const float ib = *inv_bg;
-    float s = oscale ? oscale[b] * ib : 1.0f;
+    const float ib = *inv_bg, s = oscale ? oscale[b] * ib : 1.0f;
     const size_t pstride = (size_t)B * ldo;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* op = O + (size_t)b * ldo + c;
-    if (c_part) {       // unnormalised partials of the one-pass scoring kernel: weights e^{c_p - M}, normalised by their numerator sums
-        float M = -INFINITY;
-        for (int pp = 0; pp < n_parts; ++pp) M = fmaxf(M, c_part[(size_t)pp * B + b]);
-        float D = 0.f;
-        for (int pp = 0; pp < n_parts; ++pp) {
-            const float e = expf(c_part[(size_t)pp * B + b] - M);
-            float l = 0.f;
-            for (int sb = 0; sb < n_sub; ++sb) l += l_part[((size_t)pp * n_sub + sb) * B + b];
-            D = fmaf(e, l, D);
-            const float4 v = *reinterpret_cast<const float4*>(op + pp * pstride);
-            o.x = fmaf(e, v.x, o.x); o.y = fmaf(e, v.y, o.y); o.z = fmaf(e, v.z, o.z); o.w = fmaf(e, v.w, o.w);
+    // partial sums in a fixed order, four loads in flight (a training step at the C2 shape has 37 item splits)
+    for (int p0 = 0; p0 < n_parts; p0 += 4) {
+        float4 v[4]; float w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool ok = p0 + q < n_parts;
+            v[q] = ok ? *reinterpret_cast<const float4*>(op + (size_t)(p0 + q) * pstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[q] = (ok && w_part) ? w_part[(size_t)(p0 + q) * B + b] : 1.0f;
         }
-        s /= D;
-    } else {
-        for (int pp = 0; pp < n_parts; ++pp) {
-            const float4 v = *reinterpret_cast<const float4*>(op + pp * pstride);
-            o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (p0 + q < n_parts) { o.x = fmaf(w[q], v[q].x, o.x); o.y = fmaf(w[q], v[q].y, o.y); o.z = fmaf(w[q], v[q].z, o.z); o.w = fmaf(w[q], v[q].w, o.w); }
         }
     }
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t js = indptr[u], je = indptr[u + 1];
-    for (int64_t j = js; j < je; ++j) {
-        const float x = values ? values[j] : 1.0f;
-        const float4 e = load4<T>(E + (size_t)indices[j] * lde, c, d);
-        a.x = fmaf(x, e.x, a.x); a.y = fmaf(x, e.y, a.y); a.z = fmaf(x, e.z, a.z); a.w = fmaf(x, e.w, a.w);
+    for (int64_t j = js; j < je; j += 4) {       // four E rows in flight, entries accumulated in CSR order
+        const int n = (int)min((int64_t)4, je - j);
+        int id[4]; float x[4]; float4 e[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { id[q] = q < n ? indices[j + q] : 0; x[q] = (values && q < n) ? values[j + q] : 1.0f; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e[q] = q < n ? load4<T>(E + (size_t)id[q] * lde, c, d) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q < n) { a.x = fmaf(x[q], e[q].x, a.x); a.y = fmaf(x[q], e[q].y, a.y); a.z = fmaf(x[q], e[q].z, a.z); a.w = fmaf(x[q], e[q].w, a.w); }
+        }
     }
     float4 g;
     g.x = c < d ? s * o.x - ib * a.x : 0.f;
@@ -176,26 +176,39 @@ __global__ void __launch_bounds__(256) sparse_dot_xsum_bf16_kernel(const int64_t
     }
     float acc = 0.f, xs = 0.f;
     const int64_t js = indptr[u], je = indptr[u + 1];
-    for (int64_t j = js; j < je; ++j) {
-        const float x = values ? values[j] : 1.0f;
-        const __nv_bfloat16* e = E + (size_t)indices[j] * lde;
-        float p = 0.f;
+    for (int64_t j = js; j < je; j += 4) {       // four E rows in flight per trip; same accumulation order as one by one
+        const int n = (int)min((int64_t)4, je - j);
+        int id[4]; float x[4]; uint4 w[4][4];
 #pragma unroll
-        for (int pss = 0; pss < 4; ++pss) {
-            const int ch = lane + 32 * pss;
-            if (ch < nchunks) {
-                const uint4 w = __ldg(reinterpret_cast<const uint4*>(e + ch * 8));
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        for (int q = 0; q < 4; ++q) { id[q] = q < n ? indices[j + q] : 0; x[q] = (values && q < n) ? values[j + q] : 1.0f; }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[q]));
-                    p = fmaf(ur[pss][2 * q], f.x, p);
-                    p = fmaf(ur[pss][2 * q + 1], f.y, p);
-                }
+        for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat16* e = E + (size_t)id[q] * lde;
+#pragma unroll
+            for (int pss = 0; pss < 4; ++pss) {
+                const int ch = lane + 32 * pss;
+                w[q][pss] = (q < n && ch < nchunks) ? __ldg(reinterpret_cast<const uint4*>(e + ch * 8)) : make_uint4(0, 0, 0, 0);
             }
         }
-        acc = fmaf(x, p, acc);
-        xs += x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q >= n) continue;
+            float p = 0.f;
+#pragma unroll
+            for (int pss = 0; pss < 4; ++pss) {
+                if (lane + 32 * pss < nchunks) {
+                    const uint32_t ww[4] = {w[q][pss].x, w[q][pss].y, w[q][pss].z, w[q][pss].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[k]));
+                        p = fmaf(ur[pss][2 * k], f.x, p);
+                        p = fmaf(ur[pss][2 * k + 1], f.y, p);
+                    }
+                }
+            }
+            acc = fmaf(x[q], p, acc);
+            xs += x[q];
+        }
     }
     acc = warp_sum(acc);
     if (lane == 0) { dot[b] = acc; xsum[b] = xs; }
@@ -543,17 +556,17 @@ int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const fl
 }
 
 int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B, const float* O,
-                     int ldo, int n_parts, const float* oscale, const float* c_part, const float* l_part, int n_sub, const void* E, int lde,
-                     int d, int is_bf16, const float* inv_bg, float* dU, int lddu, void* stream) {
+                     int ldo, int n_parts, const float* oscale, const float* w_part, const void* E, int lde, int d, int is_bf16,
+                     const float* inv_bg, float* dU, int lddu, void* stream) {
     if (B == 0) return 0;
     HVAE_REQUIRE(lddu % 4 == 0 && ldo % 4 == 0 && (!is_bf16 || lde % 8 == 0), "du_finalize: leading dimensions must be multiples of 4 (bf16 E: 8)");
     const int nb = ceil_div(B * (lddu / 4), 256);
     if (is_bf16)
         launch_pdl(du_finalize_kernel<__nv_bfloat16>, nb, 256, 0, (cudaStream_t)stream, 
-            indptr, indices, values, rows, B, O, ldo, n_parts, oscale, c_part, l_part, n_sub, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
+            indptr, indices, values, rows, B, O, ldo, n_parts, oscale, w_part, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
     else
         launch_pdl(du_finalize_kernel<float>, nb, 256, 0, (cudaStream_t)stream, indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
-                   c_part, l_part, n_sub, (const float*)E, lde, d, inv_bg, dU, lddu);
+                   w_part, (const float*)E, lde, d, inv_bg, dU, lddu);
     HVAE_LAUNCH_CHECK("du_finalize");
     return 0;
 }

@@ -44,12 +44,14 @@ struct StatsParams {
     const int32_t* rows;     // user ids of the batch rows (null = identity)
 };
 
-// One-pass mode (hvae_tc_score_onepass): softmax numerators are taken against a per-row shift c_b that is known BEFORE the
-// sweep instead of the row's log-sum-exp: c_b = max of the row's scores against a few probe items (cast kernel), hence
-// c_b <= max_i S_bi and the row's largest numerator is >= 1 -- nothing relevant can underflow.  The other direction is
-// checked: a row whose numerators sum beyond kOnepassOverflow (or to inf) repeats the sweep with c_b + kOnepassRetry.
-// fp32 and bf16 share the exponent range, so sum_i exp(S_bi - c_b) and sum_i exp(S_bi - c_b) E_i lose nothing.
-constexpr float kOnepassRetry = 60.0f, kOnepassOverflow = 1.2676506e30f /* 2^100 */;
+// One-pass mode (hvae_tc_score_onepass): softmax numerators are taken against a per-row shift c_b that does not depend on the
+// scores (0 to begin with) instead of the row's log-sum-exp, so no forward pass has to come first.  fp32 and bf16 share the
+// exponent range: as long as the row's numerators sum to something inside [kOnepassUnder, kOnepassOver] neither the largest
+// one overflowed nor any relevant one (>= 2^-24 of the largest, N <= 2^26) was flushed, and sum_i exp(S_bi - c_b) /
+// sum_i exp(S_bi - c_b) E_i lose nothing.  Otherwise (|scores| beyond ~70: a degenerate model, but it must stay exact) the CTA
+// repeats its sweep with c_b -+ kOnepassRetry for the rows concerned; the windows of consecutive shifts overlap widely.
+constexpr float kOnepassRetry = 60.0f, kOnepassOver = 1.2676506e30f /* 2^100 */, kOnepassUnder = 8.8817842e-16f /* 2^-50 */;
+constexpr int kOnepassMaxSweeps = 64;
 
 struct __align__(8) PipeBarriers {
     uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
@@ -281,57 +283,32 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int co
     dst[i] = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
 }
 
-// Same cast, one warp per row, plus shift[r] = max_j <bf16 row r, E_j> over the first n_probe items: a lower bound of the row's
-// largest score, the fixed softmax shift of the one-pass scoring kernel (see kOnepassRetry above).
-constexpr int kMaxProbe = 8;
-__global__ void __launch_bounds__(256) cast_bf16_probe_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
-                                                              __nv_bfloat16* __restrict__ dst, int ld_dst,
-                                                              const __nv_bfloat16* __restrict__ E, int lde, int n_probe,
-                                                              float* __restrict__ shift) {
+// Combination of the one-pass kernel's per-split results of one row (shift c_p, numerator sums l_part[p][sub]), one warp per
+// row, lanes over the splits:  M = max_p c_p (all c_p are equal unless a split had to repeat its sweep),
+// D = sum_p e^{c_p - M} sum_sub l_part,  lse_b = M + log D,  w_part[p][b] = e^{c_p - M} / D  -- hvae_du_finalize then forms
+// O_b = sum_p w_part[p][b] Opart[p][b].
+__global__ void __launch_bounds__(256) onepass_combine_kernel(const float* __restrict__ c_part, const float* __restrict__ l_part,
+                                                              int n_parts, int n_sub, int B, float* __restrict__ lse,
+                                                              float* __restrict__ w_part) {
     pdl_prologue();
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (r >= rows) return;
-    float acc[kMaxProbe];
-#pragma unroll
-    for (int j = 0; j < kMaxProbe; ++j) acc[j] = 0.f;
-    for (int c = lane; c < ld_dst; c += 32) {
-        const __nv_bfloat16 h = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
-        dst[(size_t)r * ld_dst + c] = h;
-        const float f = __bfloat162float(h);
-        if (c < cols) {
-#pragma unroll
-            for (int j = 0; j < kMaxProbe; ++j)
-                if (j < n_probe) acc[j] = fmaf(f, __bfloat162float(E[(size_t)j * lde + c]), acc[j]);
-        }
-    }
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < kMaxProbe; ++j) {
-        float a = acc[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (j < n_probe) m = fmaxf(m, a);
-    }
-    if (lane == 0) shift[r] = n_probe > 0 ? m : 0.f;
-}
-
-// lse of the one-pass kernel's per-split results (shift c_p, numerator sums l_part[p][sub]) of every row:
-// lse_b = M + log sum_p exp(c_p - M) sum_sub l_part, M = max_p c_p (all c_p are equal unless a split had to repeat its sweep).
-// hvae_du_finalize applies the same weights to the unnormalised O partials.
-__global__ void __launch_bounds__(128) onepass_lse_kernel(const float* __restrict__ c_part, const float* __restrict__ l_part,
-                                                          int n_parts, int n_sub, int B, float* __restrict__ lse) {
-    pdl_prologue();
-    const int b = blockIdx.x * 128 + threadIdx.x;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     float M = -INFINITY;
-    for (int pp = 0; pp < n_parts; ++pp) M = fmaxf(M, c_part[(size_t)pp * B + b]);
+    for (int pp = lane; pp < n_parts; pp += 32) M = fmaxf(M, c_part[(size_t)pp * B + b]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
     float D = 0.f;
-    for (int pp = 0; pp < n_parts; ++pp) {
+    for (int pp = lane; pp < n_parts; pp += 32) {
         float l = 0.f;
         for (int sb = 0; sb < n_sub; ++sb) l += l_part[((size_t)pp * n_sub + sb) * B + b];
         D = fmaf(expf(c_part[(size_t)pp * B + b] - M), l, D);
     }
-    lse[b] = M + logf(D);
+    // fixed-order reduction (xor tree): the same bits on every run
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) D += __shfl_xor_sync(0xffffffffu, D, o);
+    const float inv = 1.0f / D;
+    for (int pp = lane; pp < n_parts; pp += 32) w_part[(size_t)pp * B + b] = expf(c_part[(size_t)pp * B + b] - M) * inv;
+    if (lane == 0) lse[b] = M + logf(D);
 }
 
 
@@ -341,8 +318,8 @@ __global__ void __launch_bounds__(128) onepass_lse_kernel(const float* __restric
 // 128-item tile:  G1: S = U E_t^T (K = d, accumulators in TMEM)  ->  registers: P = exp(S - lse_b) -> bf16 -> smem
 // (128B-swizzled, K-major)  ->  G2: O += P E_t (K = 128 items; B operand = the same E rows read MN-major).
 // One CTA = (128 users, <=384 columns of O, a range of item tiles).  No gradient for E (frozen buffer).
-// One-pass mode (P.shift != null): the same sweep also IS the forward pass -- numerators against the fixed shift, their row
-// sums to l_part, O left unnormalised; a row that overflows makes its CTA (pair) repeat the sweep with a larger shift.
+// One-pass mode (P.c_part != null): the same sweep also IS the forward pass -- numerators against the fixed shift, their row
+// sums to l_part, O left unnormalised; a row outside the safe range makes its CTA (pair) repeat the sweep with another shift.
 constexpr int G_BN = 128;                     // items per tile
 constexpr int G_STAGES = 4, G_SLOT = 32768;   // ring slot: U [128x64] + E [128x64] for G1, or E [64 x <=256] for G2
 constexpr int G_DCHUNK = 384;                 // O columns per CTA (TMEM: 384 O + 128 S = 512)
@@ -358,9 +335,8 @@ struct GradParams {
     float* lse_out;       // [B]
     float* Opart;         // [n_splits][B][ldo]
     int ldo;
-    // one-pass mode
-    const float* shift;   // [B] initial shift per row (<= the row's largest score), or null = two-pass mode above
-    float* c_part;        // [n_splits][B]  shift finally used by the split
+    // one-pass mode (c_part != null)
+    float* c_part;        // [n_splits][B]  shift the split ended up with
     float* l_part;        // [n_splits][n_sub][B]  row sums of the numerators (n_sub = 2 for the pair kernel: one per CTA)
 };
 
@@ -397,7 +373,7 @@ __device__ __forceinline__ float softmax_tile(const float (&v)[4][32], float shi
 struct __align__(8) GradBarriers {
     uint64_t full[G_STAGES], empty[G_STAGES], s_full, s_free, p_full[2], p_free[2], o_full;
     uint32_t tmem_base;
-    uint8_t retry[2][BM];     // pair kernel: per-row "sweep overflowed" flags of both CTAs (each CTA holds both arrays)
+    float rsum[2][BM];        // pair kernel: the row sums of both CTAs' sweeps (each CTA holds both arrays)
 };
 
 // Row r of the merged forward partials (two-pass mode without a ready lse).
@@ -445,7 +421,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
     const uint32_t tmem_base = bars->tmem_base;
     pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
     const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
-    const bool onepass = P.shift != nullptr;
+    const bool onepass = P.c_part != nullptr;
 
     // epilogue state (warps 2..5): thread <-> user row
     const int q = warp & 3;
@@ -454,9 +430,8 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
     const bool row_ok = warp >= 2 && row < P.B;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
     float lse_row = 0.f;      // two-pass: the row's log-sum-exp; one-pass: the shift
-    if (row_ok) {
-        if (onepass) lse_row = P.shift[row];
-        else if (P.lse) lse_row = P.lse[row];
+    if (row_ok && !onepass) {
+        if (P.lse) lse_row = P.lse[row];
         else {                 // merge the forward partials here instead of in a separate launch
             lse_row = merged_lse(P.part_m, P.part_l, P.lse_splits, row);
             if (chunk == 0 && split == 0) P.lse_out[row] = lse_row;
@@ -577,9 +552,10 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
         }
         __syncwarp();
         if (!onepass) break;
-        const bool over = warp >= 2 && lsum > kOnepassOverflow;      // inf included; NaN is not (it propagates, as in the reference)
-        if (!__syncthreads_or(over)) break;
-        if (over) lse_row += kOnepassRetry;
+        const bool over = warp >= 2 && lsum > kOnepassOver;          // inf included; NaN is not (it propagates, as in the reference)
+        const bool under = warp >= 2 && lsum < kOnepassUnder;
+        if (!__syncthreads_or(over || under) || sweep + 1 >= kOnepassMaxSweeps) break;
+        lse_row += over ? kOnepassRetry : under ? -kOnepassRetry : 0.f;
     }
     if (warp >= 2) {
         // ---- O (TMEM) -> global partial ---------------------------------------------------------------------
@@ -658,7 +634,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
     const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
     auto own = [&](int ti) { return (uint32_t)(ti & 1) == rank; };
     auto uses = [&](int b) { return (T + 1 - b) >> 1; };              // tiles of parity b per sweep
-    const bool onepass = P.shift != nullptr;
+    const bool onepass = P.c_part != nullptr;
 
     const int q = warp & 3;
     const int r_local = q * 32 + lane;
@@ -666,9 +642,8 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
     const bool row_ok = warp >= 2 && row < P.B;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
     float lse_row = 0.f;      // two-pass: the row's log-sum-exp; one-pass: the shift
-    if (row_ok) {
-        if (onepass) lse_row = P.shift[row];
-        else if (P.lse) lse_row = P.lse[row];
+    if (row_ok && !onepass) {
+        if (P.lse) lse_row = P.lse[row];
         else {
             lse_row = merged_lse(P.part_m, P.part_l, P.lse_splits, row);
             if (chunk == 0 && split == 0) P.lse_out[row] = lse_row;
@@ -798,17 +773,18 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
         }
         __syncwarp();
         if (!onepass) break;
-        // a row overflowed in either CTA (each saw only its own tiles) -> both repeat the sweep with the same larger shift
+        // each CTA saw only its own tiles: the decision is taken on the pair's sum, identically in both CTAs
         if (warp >= 2) {
-            const uint8_t f = lsum > kOnepassOverflow ? 1 : 0;
-            bars->retry[rank][r_local] = f;
-            const uint32_t remote = map_to_cta(smem_u32(&bars->retry[rank][r_local]), peer);
-            asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(remote), "r"((uint32_t)f) : "memory");
+            bars->rsum[rank][r_local] = lsum;
+            const uint32_t remote = map_to_cta(smem_u32(&bars->rsum[rank][r_local]), peer);
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(lsum) : "memory");
         }
         cluster_sync_all();
-        const bool over = warp >= 2 && (bars->retry[0][r_local] | bars->retry[1][r_local]) != 0;
-        if (!__syncthreads_or(over)) break;
-        if (over) lse_row += kOnepassRetry;
+        const float both = warp >= 2 ? bars->rsum[0][r_local] + bars->rsum[1][r_local] : 1.0f;
+        const bool over = both > kOnepassOver, under = both < kOnepassUnder;
+        if (!__syncthreads_or(over || under) || sweep + 1 >= kOnepassMaxSweeps) break;
+        lse_row += over ? kOnepassRetry : under ? -kOnepassRetry : 0.f;
+        cluster_sync_all();            // the peer has read this sweep's sums before the next sweep's overwrite them
     }
     if (warp >= 2) {
         // ---- O (TMEM) -> global partial ---------------------------------------------------------------------
@@ -839,7 +815,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
     }
 }
 
-constexpr size_t kGradSmem = G_STAGES * G_SLOT + 2 * G_PBYTES + 512 + 1024;
+constexpr size_t kGradSmem = G_STAGES * G_SLOT + 2 * G_PBYTES + 1536 + 1024;
 
 // Item splits per (user tile, column chunk): one CTA per SM in a single wave when each CTA would otherwise get only a
 // few tiles (the prologue -- barrier init, TMEM alloc, first TMA -- costs about one tile), two waves for long CTAs.
@@ -952,7 +928,7 @@ static bool grad_is_pair(int d) {
 
 static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, const float* part_m,
                        const float* part_l, int lse_splits, float* lse_out, float* Opart, int ldo, cudaStream_t stream,
-                       const float* shift = nullptr, float* c_part = nullptr, float* l_part = nullptr) {
+                       float* c_part = nullptr, float* l_part = nullptr) {
     HVAE_REQUIRE(ldo % 4 == 0 && ldo >= d, "tc_score_grad: bad ldo=%d for d=%d", ldo, d);
     CUtensorMap tmU, tmE;
     if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
@@ -961,7 +937,7 @@ static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, in
     GradParams P{};
     P.B = B; P.N = N; P.d = d; P.lse = lse; P.part_m = part_m; P.part_l = part_l; P.lse_splits = lse_splits; P.lse_out = lse_out;
     P.Opart = Opart; P.ldo = ldo;
-    P.shift = shift; P.c_part = c_part; P.l_part = l_part;
+    P.c_part = c_part; P.l_part = l_part;
     P.n_splits = pick_grad_splits(m_tiles, n_chunks, n_tiles);
     P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
     static bool attr_set = false;
@@ -1040,34 +1016,26 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
 }
 
 
-int hvae_cast_bf16_probe(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, const void* E, int lde, int N,
-                         float* shift, void* stream) {
-    if (rows == 0) return 0;
-    launch_pdl(cast_bf16_probe_kernel, ceil_div(rows, 8), 256, 0, (cudaStream_t)stream, src, rows, cols, ld_src, (__nv_bfloat16*)dst, ld_dst,
-               (const __nv_bfloat16*)E, lde, min(N, kMaxProbe), shift);
-    HVAE_LAUNCH_CHECK("cast_bf16_probe");
-    return 0;
-}
-
 // 1 or 2 numerator sums per (split, row): the pair kernel's two CTAs each report the tiles they owned
 size_t hvae_tc_onepass_subparts(int d) { return grad_is_pair(d) ? 2 : 1; }
 
 // Forward and backward through the scores in ONE sweep over the items (4 B N d executed flops instead of the 6 B N d of
-// hvae_tc_score_lse_grad): the backward kernel takes the softmax numerators against the fixed per-row shift (a lower bound of
-// the row's largest score, hvae_cast_bf16_probe) and also returns their row sums.  Opart then holds UNNORMALISED sums;
-// hvae_du_finalize combines them with (c_part, l_part), hvae_tc_onepass_lse gives the log-sum-exp.
-int hvae_tc_score_onepass(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* shift, float* c_part,
-                          float* l_part, float* Opart, int ldo, void* stream) {
+// hvae_tc_score_lse_grad): the backward kernel takes the softmax numerators against a score-independent shift and also returns
+// their row sums.  Opart then holds UNNORMALISED sums; hvae_tc_onepass_combine turns (c_part, l_part) into the log-sum-exp and
+// the weights hvae_du_finalize applies to the partials.
+int hvae_tc_score_onepass(const void* U, int ldu, int B, const void* E, int lde, int N, int d, float* c_part, float* l_part,
+                          float* Opart, int ldo, void* stream) {
     if (B == 0) return 0;
     HVAE_REQUIRE(N > 0 && d > 0, "tc_score_onepass: empty catalogue");
-    HVAE_REQUIRE(shift && c_part && l_part, "tc_score_onepass: shift / c_part / l_part are required");
-    return launch_grad(U, ldu, B, E, lde, N, d, nullptr, nullptr, nullptr, 0, nullptr, Opart, ldo, (cudaStream_t)stream, shift, c_part, l_part);
+    HVAE_REQUIRE(c_part && l_part, "tc_score_onepass: c_part / l_part are required");
+    return launch_grad(U, ldu, B, E, lde, N, d, nullptr, nullptr, nullptr, 0, nullptr, Opart, ldo, (cudaStream_t)stream, c_part, l_part);
 }
 
-int hvae_tc_onepass_lse(const float* c_part, const float* l_part, int n_parts, int n_sub, int B, float* lse, void* stream) {
+int hvae_tc_onepass_combine(const float* c_part, const float* l_part, int n_parts, int n_sub, int B, float* lse, float* w_part,
+                            void* stream) {
     if (B == 0) return 0;
-    launch_pdl(onepass_lse_kernel, ceil_div(B, 128), 128, 0, (cudaStream_t)stream, c_part, l_part, n_parts, n_sub, B, lse);
-    HVAE_LAUNCH_CHECK("tc_onepass_lse");
+    launch_pdl(onepass_combine_kernel, ceil_div(B, 8), 256, 0, (cudaStream_t)stream, c_part, l_part, n_parts, n_sub, B, lse, w_part);
+    HVAE_LAUNCH_CHECK("tc_onepass_combine");
     return 0;
 }
 

@@ -455,9 +455,9 @@ class Engine:
             is_bf16 = 0 if self.precision == "fp32" else 1
             Eg, lde = (self.E, d) if not is_bf16 else (self.E_bf16, r8(d))
             n_parts = O.shape[0] if O.dim() == 3 else 1
-            oscale, c_part, l_part, n_sub = oscale if isinstance(oscale, tuple) else (oscale, None, None, 0)
-            lib.du_finalize(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(O), ldd, n_parts, p(oscale), p(c_part),
-                            p(l_part), n_sub, p(Eg), lde, d, is_bf16, self.state_ptr("inv_bg"), p(dU), ldd, st)
+            oscale, w_part = oscale if isinstance(oscale, tuple) else (oscale, None)
+            lib.du_finalize(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(O), ldd, n_parts, p(oscale), p(w_part),
+                            p(Eg), lde, d, is_bf16, self.state_ptr("inv_bg"), p(dU), ldd, st)
         if lay.identity_proj:
             dz = dU
         else:

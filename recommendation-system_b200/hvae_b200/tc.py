@@ -16,15 +16,10 @@ from .engine import r4, r8
 MAX_K_TC = 32
 
 
-def user_vectors_bf16(eng, u, B, shift=None):
-    """bf16 copy of the user vectors; shift (optional, [B]) receives each row's best score among the first 8 items (the
-    softmax shift of the one-pass scoring kernel: a lower bound of the row's largest score)."""
+def user_vectors_bf16(eng, u, B):
     d = eng.lay.d
     ub = eng.ws.get("u_bf16", (B, r8(d)), torch.bfloat16)
-    if shift is None:
-        eng.lib.cast_bf16(p(u), B, d, r4(d), p(ub), r8(d), eng.stream)
-    else:
-        eng.lib.cast_bf16_probe(p(u), B, d, r4(d), p(ub), r8(d), p(eng.E_bf16), r8(d), eng.lay.N, p(shift), eng.stream)
+    eng.lib.cast_bf16(p(u), B, d, r4(d), p(ub), r8(d), eng.stream)
     return ub
 
 
@@ -32,16 +27,15 @@ def score_loss_bf16(eng, batch, u, want_grad):
     """-> (lse [B], dot [B], xsum [B], O partial sums [splits, B, ld] or None, per-row scale(s) of O).
 
     Training (want_grad) runs the one-pass kernel: forward and backward through the scores in a single sweep over the
-    items (softmax numerators against a shift known beforehand, hvae_tc_score_onepass); O is then unnormalised and its
-    scale is (xsum, c_part, l_part, n_sub).  HVAE_TWO_PASS=1 selects the forward-LSE + backward pair of launches instead."""
+    items (softmax numerators against a score-independent shift, hvae_tc_score_onepass); O is then unnormalised and its
+    scale is (xsum, w_part).  HVAE_TWO_PASS=1 selects the forward-LSE + backward pair of launches instead."""
     lay, ws, lib, st = eng.lay, eng.ws, eng.lib, eng.stream
     B, N, d = batch.B, lay.N, lay.d
     ldd, ld8 = r4(d), r8(d)
     csr = batch.csr
     Eb = eng.E_bf16
     onepass = want_grad and not eng.two_pass
-    shift = ws.get("tc_shift", (B,)) if onepass else None
-    ub = user_vectors_bf16(eng, u, B, shift)
+    ub = user_vectors_bf16(eng, u, B)
     lse, dot, xsum = ws.get("lse", (B,)), ws.get("dot", (B,)), ws.get("xsum", (B,))
     with eng.side(1):                # independent of the score GEMMs
         lib.sparse_dot_xsum(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(ub), ld8, p(Eb), ld8, d, 1,
@@ -53,12 +47,11 @@ def score_loss_bf16(eng, batch, u, want_grad):
         gs = int(lib.tc_grad_splits(B, N, d))
         O = ws.get("tc_O", (gs, B, ldd))
         n_sub = int(lib.tc_onepass_subparts(d))
-        c_part, l_part = ws.get("tc_c_part", (gs, B)), ws.get("tc_l_part", (gs, n_sub, B))
+        c_part, l_part, w_part = ws.get("tc_c_part", (gs, B)), ws.get("tc_l_part", (gs, n_sub, B)), ws.get("tc_w_part", (gs, B))
         with eng.span("score_onepass"):
-            lib.tc_score_onepass(p(ub), ld8, B, p(Eb), ld8, N, d, p(shift), p(c_part), p(l_part), p(O), ldd, st)
-        with eng.side(1):            # only the loss scalars need lse: off the critical path (du_finalize applies the weights itself)
-            lib.tc_onepass_lse(p(c_part), p(l_part), gs, n_sub, B, p(lse), eng.stream)
-        return lse, dot, xsum, O, (xsum, c_part, l_part, n_sub)
+            lib.tc_score_onepass(p(ub), ld8, B, p(Eb), ld8, N, d, p(c_part), p(l_part), p(O), ldd, st)
+            lib.tc_onepass_combine(p(c_part), p(l_part), gs, n_sub, B, p(lse), p(w_part), st)
+        return lse, dot, xsum, O, (xsum, w_part)
     if want_grad and eng.prof is None:        # two launches: the backward kernel merges the forward partials itself
         gs = int(lib.tc_grad_splits(B, N, d))
         O = ws.get("tc_O", (gs, B, ldd))

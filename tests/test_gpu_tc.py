@@ -128,33 +128,27 @@ def _onepass(lib, dev, U, E, st):
     B, d = U.shape
     N = E.shape[0]
     Eb, lde = _cast(lib, E.contiguous(), dev)
-    ldu = _r8(d)
-    Ub = torch.empty(B, ldu, dtype=torch.bfloat16, device=dev)
-    shift = torch.empty(B, device=dev)
-    lib.cast_bf16_probe(U.contiguous().data_ptr(), B, d, d, Ub.data_ptr(), ldu, Eb.data_ptr(), lde, N, shift.data_ptr(), st)
-    assert torch.equal(Ub[:, :d], U.to(torch.bfloat16)) and torch.all(Ub[:, d:] == 0)
+    Ub, ldu = _cast(lib, U.contiguous(), dev)
     S = Ub[:, :d].float().double() @ Eb[:, :d].float().double().t()
-    np.testing.assert_allclose(shift.cpu().numpy(), S[:, :min(N, 8)].max(dim=1).values.cpu().numpy(), rtol=1e-5, atol=1e-5)
     gs = int(lib.tc_grad_splits(B, N, d))
     n_sub = int(lib.tc_onepass_subparts(d))
     ldo = (d + 3) // 4 * 4
     Op = torch.full((gs, B, ldo), float("nan"), device=dev)
     c_part = torch.full((gs, B), float("nan"), device=dev)
     l_part = torch.full((gs, n_sub, B), float("nan"), device=dev)
+    w_part = torch.full((gs, B), float("nan"), device=dev)
     lse = torch.full((B,), float("nan"), device=dev)
-    lib.tc_score_onepass(Ub.data_ptr(), ldu, B, Eb.data_ptr(), lde, N, d, shift.data_ptr(), c_part.data_ptr(), l_part.data_ptr(),
-                         Op.data_ptr(), ldo, st)
-    lib.tc_onepass_lse(c_part.data_ptr(), l_part.data_ptr(), gs, n_sub, B, lse.data_ptr(), st)
-    # the combination hvae_du_finalize applies: O = sum_p e^{c_p - M} O_p / sum_p e^{c_p - M} l_p   (checked through the C ABI
-    # itself with an empty interaction matrix and oscale = 1, 1/Bg = 1)
+    lib.tc_score_onepass(Ub.data_ptr(), ldu, B, Eb.data_ptr(), lde, N, d, c_part.data_ptr(), l_part.data_ptr(), Op.data_ptr(), ldo, st)
+    lib.tc_onepass_combine(c_part.data_ptr(), l_part.data_ptr(), gs, n_sub, B, lse.data_ptr(), w_part.data_ptr(), st)
+    # O = sum_p w_p O_p through the C ABI itself: hvae_du_finalize with an empty interaction matrix, oscale = 1 and 1/Bg = 1
     ip = torch.zeros(B + 1, dtype=torch.int64, device=dev)
     ix = torch.zeros(1, dtype=torch.int32, device=dev)
     one = torch.ones(B, device=dev)
     inv_bg = torch.ones(1, device=dev)
     dU = torch.empty(B, ldo, device=dev)
-    lib.du_finalize(ip.data_ptr(), ix.data_ptr(), None, None, B, Op.data_ptr(), ldo, gs, one.data_ptr(), c_part.data_ptr(), l_part.data_ptr(),
-                    n_sub, Eb.data_ptr(), lde, d, 1, inv_bg.data_ptr(), dU.data_ptr(), ldo, st)
-    return lse, dU[:, :d].double(), c_part, shift, S, Eb[:, :d].float().double()
+    lib.du_finalize(ip.data_ptr(), ix.data_ptr(), None, None, B, Op.data_ptr(), ldo, gs, one.data_ptr(), w_part.data_ptr(), Eb.data_ptr(), lde,
+                    d, 1, inv_bg.data_ptr(), dU.data_ptr(), ldo, st)
+    return lse, dU[:, :d].double(), c_part, S, Eb[:, :d].float().double()
 
 
 @pytest.mark.parametrize("B,N,d", [(512, 12101, 384), (128, 256, 64), (77, 1000, 64), (300, 5000, 768), (130, 890, 384), (64, 300, 24),
@@ -165,8 +159,8 @@ def test_tc_onepass_matches_torch(dev, B, N, d):
     lib = _cabi.lib()
     st = torch.cuda.current_stream().cuda_stream
     U, E = _operands(B, N, d, dev, seed=2)
-    lse, O, c_part, shift, S, Ed = _onepass(lib, dev, U, E, st)
-    assert torch.equal(c_part, shift[None, :].expand_as(c_part))               # no sweep had to be repeated
+    lse, O, c_part, S, Ed = _onepass(lib, dev, U, E, st)
+    assert bool((c_part == 0).all())                                           # no sweep had to be repeated
     np.testing.assert_allclose(lse.cpu().numpy(), torch.logsumexp(S, dim=1).cpu().numpy(), rtol=2e-6, atol=2e-5)
     ref = torch.softmax(S, dim=1) @ Ed
     scale = float(ref.abs().max())
@@ -174,25 +168,28 @@ def test_tc_onepass_matches_torch(dev, B, N, d):
     assert float((O - ref).abs().max()) < 1e-2 * scale + 1e-6                 # bf16 rounding of the numerators
 
 
-def test_tc_onepass_overflow_retry(dev):
-    """Rows whose largest score lies far above the probe's: the sweep overflows and is repeated with a larger shift -- by the
-    splits that saw the overflow only, so the per-split shifts differ and the combination has to weight them; peaked, flat
-    and all-zero rows in the same batch."""
+def test_tc_onepass_retry(dev):
+    """Rows whose scores leave the window of the initial shift (largest score beyond ~ +70, or everything below ~ -35): the
+    sweep is repeated with a moved shift -- only by the splits that saw the problem, so the per-split shifts differ and the
+    combination has to weight them; peaked, flat and all-zero rows in the same batch."""
     from hvae_b200 import _cabi
     lib = _cabi.lib()
     st = torch.cuda.current_stream().cuda_stream
     for d, N in ((384, 3001), (768, 2500), (64, 40000)):
         B = 300                                                               # three user tiles
         U, E = _operands(B, N, d, dev, seed=5)
+        v = torch.nn.functional.normalize(torch.ones(d, device=dev), dim=0)
+        E = torch.nn.functional.normalize(E + 3.0 * v, dim=1)                 # every item shares a direction: cos(E_i, v) ~ 0.95
         U = U / U.norm(dim=1, keepdim=True) * 6.0
-        U[3] = 48.0 * E[17]                                                   # very peaked, but within the first window
-        U[130] = 150.0 * E[N - 5]                                             # S_max = 150 at the end of the catalogue: two retries
-        U[131] = 100.0 * E[N // 2] - 100.0 * E[0]                             # probe far below the maximum
-        U[7] = 500.0 * E[33]                                                  # many retries
+        U[3] = 48.0 * E[17]                                                   # large scores, but inside the first window
+        U[130] = 150.0 * E[N - 5]                                             # S_max = 150 at the end of the catalogue: overflow
+        U[7] = 500.0 * E[33]                                                  # many repeats
+        U[131] = -100.0 * v                                                   # every score ~ -95: everything would be flushed
         U[260] = 0.0                                                          # uniform softmax
-        lse, O, c_part, shift, S, Ed = _onepass(lib, dev, U, E, st)
-        moved = (c_part != shift[None, :]).any(dim=0).cpu()
-        assert bool(moved[130]) and bool(moved[131]) and bool(moved[7]) and not bool(moved[260]) and not bool(moved[200])
+        lse, O, c_part, S, Ed = _onepass(lib, dev, U, E, st)
+        moved = (c_part != 0).any(dim=0).cpu()
+        assert bool(moved[130]) and bool(moved[7]) and bool(moved[131])
+        assert not bool(moved[260]) and not bool(moved[200]) and not bool(moved[3])
         np.testing.assert_allclose(lse.cpu().numpy(), torch.logsumexp(S, dim=1).cpu().numpy(), rtol=3e-6, atol=5e-5)
         ref = torch.softmax(S, dim=1) @ Ed
         assert torch.isfinite(O).all()
