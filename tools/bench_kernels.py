@@ -45,10 +45,17 @@ def main():
     indptr = torch.arange(0, 10 * (B + 1), 10, dtype=torch.int64, device=dev)
     indices = torch.sort(torch.randint(0, N, (B, 10), device=dev, generator=g), dim=1)[0].to(torch.int32).reshape(-1).contiguous()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    n_sub = int(lib.tc_onepass_subparts(d))
+    # S = U E^T and O = P E, 2BNd each; beyond d = 768 every 384-column chunk of O recomputes S
+    executed_bwd = 4.0 * B * N * d if d <= 768 else 2.0 * B * N * d * (1 + (d + 383) // 384)
+    c_part = torch.empty(gs, B, device=dev)
+    l_part = torch.empty(gs, n_sub, B, device=dev)
     kernels = {
+        "tc_score_onepass": (lambda: lib.tc_score_onepass(U.data_ptr(), ld, B, E.data_ptr(), ld, N, d, c_part.data_ptr(), l_part.data_ptr(),
+                                                          Op.data_ptr(), ldo, st), 4.0 * B * N * d, executed_bwd),
         "tc_score_lse": (lambda: lib.tc_score_lse(U.data_ptr(), ld, B, E.data_ptr(), ld, N, d, lse.data_ptr(), ws.data_ptr(), st), 2.0 * B * N * d, 2.0 * B * N * d),
         "tc_score_grad": (lambda: lib.tc_score_grad(U.data_ptr(), ld, B, E.data_ptr(), ld, N, d, lse.data_ptr(), Op.data_ptr(), ldo, st),
-                          2.0 * B * N * d, 2.0 * B * N * d * (1 + (d + 383) // 384)),
+                          2.0 * B * N * d, executed_bwd),
         "tc_score_topk": (lambda: lib.tc_score_topk(U.data_ptr(), ld, B, E.data_ptr(), ld, N, d, 0, indptr.data_ptr(), indices.data_ptr(), None, K,
                                                     cv.data_ptr(), ci.data_ptr(), st), 2.0 * B * N * d, 2.0 * B * N * d),
     }
