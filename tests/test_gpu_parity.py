@@ -217,6 +217,31 @@ def test_full_ranking_matches_reference(dev, name, train):
     assert ev.evaluate_user("nobody", ["i0000001"]) == {}
 
 
+def test_batched_serving_call_matches_reference(dev):
+    """The API's scoring call (src/api/server.py:142-178) through hvae_b200.serve: one launch for a group of requests gives
+    each user exactly the reference's top-100 (golden `rec100`, frozen from the reference's own evaluator)."""
+    from hvae_b200.evaluate import RecommendationEvaluator
+    from hvae_b200.serve import RecommendService, UnknownUser
+    c = Case("tiny_two_hidden")
+    g = np.load(str(GOLDEN / "tiny_two_hidden_eval.npz"))
+    m = _build(c, dev, state="final")
+    u2i = {f"u{i:07d}": i for i in range(c.n_users)}
+    i2it = {i: f"i{i:07d}" for i in range(c.n_items)}
+    ev = RecommendationEvaluator(m, c.csr, u2i, {v: k for k, v in i2it.items()}, dev, batch_users=64)
+    svc = RecommendService.from_evaluator(ev, i2it)
+    reqs = [(f"u{u:07d}", 100, True) for u in range(6)] + [("nobody", 10, True)] + [(f"u{u:07d}", 10, False) for u in range(6)]
+    out = svc.recommend_many(reqs)
+    assert isinstance(out[6], UnknownUser)
+    for u in range(6):
+        idx, score = g[f"rec100/{u}/idx"], g[f"rec100/{u}/score"]
+        keep = ~np.isinf(score)
+        assert [r["item_id"] for r in out[u]["recommendations"]] == [i2it[int(i)] for i in idx[keep]]
+        np.testing.assert_allclose([r["score"] for r in out[u]["recommendations"]], score[keep], rtol=1e-4, atol=2e-5)
+        assert out[u]["total_items"] == c.n_items and out[u]["user_id"] == f"u{u:07d}"
+        assert [r["item_id"] for r in out[7 + u]["recommendations"]] == [i2it[int(i)] for i in g[f"rec10_all/{u}/idx"]]
+        assert svc.recommend(f"u{u:07d}", 100, True) == out[u]
+
+
 def test_c1_shape_eval_matches_reference(dev):
     """Config 1 shape (2,072 x 890, d=384): untrained reference weights under torch.manual_seed(0)."""
     from hvae_b200.evaluate import RecommendationEvaluator
