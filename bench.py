@@ -304,7 +304,7 @@ def main():
                                     "achieved": 2 * flops_fwd / (span_avg["score_onepass"] * 1e-3) / 1e12, "peak": pk["tc_sustained"],
                                     "unit": "TFLOP/s", "algorithmic_flops": 2 * flops_fwd,
                                     "executed_flops": flops_fwd * (2 if d <= 768 else 1 + -(-((d + 63) // 64 * 64) // 384)),
-                                    "launches": "one-pass kernel + gated two-pass fallback (idle) + finalize"}
+                                    "launches": "one-pass scoring kernel + combine"}
     if "gather" in span_avg:
         nnz_avg = float(lens[order[:Bg * min(4, n_batches)]].sum()) / min(4, n_batches) / world
         gbytes = nnz_avg * (ld1 * 4 + 4) + B * (3 * ld1 * 4 + 16)
