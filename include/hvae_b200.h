@@ -94,6 +94,13 @@ int hvae_batch_transpose(const int64_t* indptr, const int32_t* indices, const fl
                          int32_t* overflow, void* temp, size_t temp_bytes, void* stream);
 int hvae_batch_release(const int32_t* uniq_item, const int32_t* n_unique, int cap, int32_t* slot_of_item, void* stream);
 
+/* Host <-> device plumbing of the per-step API (one batch per call, as the reference's loop, train.py:86-96): the batch's CSR
+ * slice from (pinned) host memory into the step's static device buffers (three async copies on `stream`), and n floats back
+ * (async copy, then the call waits for `stream`). */
+int hvae_h2d_csr_batch(const int64_t* h_crow, const int32_t* h_col, const float* h_val, int B, int64_t nnz, int64_t* d_crow,
+                       int32_t* d_col, float* d_val, void* stream);
+int hvae_d2h_floats(const float* d_src, int n, float* h_dst, void* stream);
+
 /* ---- dense fp32 GEMM with arbitrary strides (aten::addmm / aten::mm, SURVEY.md K2,K5,K6,K8) ------------ */
 int hvae_gemm_f32(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
                   int64_t b_cs, float* C, int64_t ldc, const float* bias, float alpha, void* stream);

@@ -164,6 +164,7 @@ class VAETrainer:
         self._noise_ctr = 0
         self._loaders = {}
         self._graphs = {}
+        self._loss_host = None      # pinned landing buffer of last_losses()
         self._anneal_dev = 0        # device copy of AnnealedVAE.current_step (hvae_step_state.anneal_step)
         self.graph_collectives = True   # data parallel: capture the NCCL exchange into the step graph as well
         logger.info("Trainer on %s, %s params", device, f"{self.model.num_parameters():,}")
@@ -383,9 +384,15 @@ class VAETrainer:
         crow, col, val = x.crow_indices(), x.col_indices(), x.values()
         nnz, B = int(col.shape[0]), x.shape[0]
         ent = self._graph_entry("csr", Batch(None, None, B, max(1, nnz)), b_global)
-        ent["crow"].copy_(crow, non_blocking=True)
-        ent["col"][:nnz].copy_(col, non_blocking=True)
-        ent["val"][:nnz].copy_(val, non_blocking=True)
+        if (crow.dtype == torch.int64 and col.dtype == torch.int32 and val.dtype == torch.float32 and crow.is_contiguous()
+                and col.is_contiguous() and val.is_contiguous()):
+            eng = self.model.engine            # the three copies behind one C call (hvae_h2d_csr_batch)
+            eng.lib.h2d_csr_batch(crow.data_ptr(), col.data_ptr(), val.data_ptr(), B, nnz, p(ent["crow"]), p(ent["col"]), p(ent["val"]),
+                                  eng.stream)
+        else:
+            ent["crow"].copy_(crow, non_blocking=True)
+            ent["col"][:nnz].copy_(col, non_blocking=True)
+            ent["val"][:nnz].copy_(val, non_blocking=True)
         self._run_entry(ent, b_global)
 
     def train_on_batch(self, x, b_global=None, nnz_cap_global=None) -> dict[str, float]:
@@ -433,8 +440,12 @@ class VAETrainer:
         return {"total_loss": float(acc[0] / n), "recon_loss": float(acc[1] / n), "kl_loss": float(acc[2] / n)}
 
     def last_losses(self):
-        """(total, recon, kl) of the most recent step (device->host read)."""
-        return tuple(float(v) for v in self.model.engine.loss_out.cpu())
+        """(total, recon, kl) of the most recent step (device->host read into pinned memory; waits for the step)."""
+        eng = self.model.engine
+        if self._loss_host is None:
+            self._loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+        eng.lib.d2h_floats(p(eng.loss_out), 3, self._loss_host.data_ptr(), eng.stream)
+        return tuple(self._loss_host.tolist())
 
     def save_checkpoint(self, path, epoch: int, is_best: bool = False, extra: dict | None = None) -> None:
         """src/ml/train.py:126-145: same keys; tensors in the reference's shapes."""
