@@ -92,7 +92,11 @@ int hvae_batch_transpose(const int64_t* indptr, const int32_t* indices, const fl
                          int32_t* eid_sorted, int32_t* head, int32_t* slot, int32_t* ent_user, float* ent_val,
                          int32_t* seg_start, int32_t* uniq_item, int32_t* slot_of_item, int32_t* n_unique,
                          int32_t* overflow, void* temp, size_t temp_bytes, void* stream);
-int hvae_batch_release(const int32_t* uniq_item, const int32_t* n_unique, int cap, int32_t* slot_of_item, void* stream);
+/* Restores slot_of_item to -1 for the step's touched items.  `overflow` (may be NULL) is hvae_batch_transpose's counter of rows
+ * that did not fit in `cap`: when non-zero the step's loss scalars `loss_out[0..2]` and accumulators `acc[0..2]` (may be NULL)
+ * are set to NaN so that a too-small nnz bound can never pass silently; the counter itself is left for the host to read/clear. */
+int hvae_batch_release(const int32_t* uniq_item, const int32_t* n_unique, int cap, int32_t* slot_of_item,
+                       const int32_t* overflow, float* loss_out, float* acc, void* stream);
 
 /* Host <-> device plumbing of the per-step API (one batch per call, as the reference's loop, train.py:86-96): the batch's CSR
  * slice from (pinned) host memory into the step's static device buffers (three async copies on `stream`), and n floats back
@@ -175,6 +179,12 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
  * (autograd of model.py:198,281; E is a frozen buffer, no dE).  lse from hvae_tc_score_lse.
  * Opart: [hvae_tc_grad_splits(B,N,d)][B][ldo] partial sums over item splits. */
 size_t hvae_tc_grad_splits(int B, int N, int d);
+/* Diagnostic: CTA pairs (clusters of 2) of the cta_group::2 scoring kernel the device holds at once with smem_bytes of dynamic
+ * shared memory per CTA (0 = the kernel's own size); < 0 = query failed. */
+int hvae_tc_duo_max_clusters(int smem_bytes);
+/* Profiling: while trace != NULL the cta_group::2 scoring kernel runs an instrumented build that writes per CTA and role
+ * (TMA producer, MMA issuer, softmax warp) 8 int64 cycle counters of its barrier waits: [2 * m_tiles * n_splits][3][8]. */
+int hvae_tc_duo_trace(int64_t* trace);
 int hvae_tc_score_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, float* Opart,
                        int ldo, void* stream);
 

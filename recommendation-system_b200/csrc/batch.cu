@@ -46,7 +46,7 @@ __global__ void expand_kernel(const int64_t* __restrict__ indptr, const int32_t*
     if (u < 0) return;  // padding slot of a data-parallel global batch
     const int64_t s = indptr[u];
     const int len = (int)(indptr[u + 1] - s), o = boff[b];
-    if (o + len > cap) { if (lane == 0) atomicExch(overflow, 1); return; }
+    if (o + len > cap) { if (lane == 0) atomicAdd(overflow, 1); return; }   // sticky: hvae_batch_release poisons the step's loss
     for (int j = lane; j < len; j += 32) {
         keys[o + j] = indices[s + j];
         ent_user[o + j] = b;
@@ -79,11 +79,20 @@ __global__ void seg_write_kernel(const int32_t* __restrict__ keys, const int32_t
     if (e == cap - 1 && k != sentinel) { *n_unique = slot[e] + head[e]; seg_start[slot[e] + head[e]] = cap; }
 }
 
+// Also the step's overflow check: if hvae_batch_transpose had to drop rows (the caller's nnz bound was too small, so the
+// layer-1 weight gradient of this step is incomplete) the step's loss scalars and the epoch accumulators become NaN -- the
+// host raises on the next loss read (hvae_b200/train.py); the counter stays set until the host clears it.
 __global__ void batch_release_kernel(const int32_t* __restrict__ uniq_item, const int32_t* __restrict__ n_unique, int cap,
-                                     int32_t* __restrict__ slot_of_item) {
+                                     int32_t* __restrict__ slot_of_item, const int32_t* __restrict__ overflow,
+                                     float* __restrict__ loss_out, float* __restrict__ acc) {
     pdl_prologue();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < cap && s < *n_unique) slot_of_item[uniq_item[s]] = -1;
+    if (s == 0 && overflow && *overflow != 0) {
+        const float qnan = __int_as_float(0x7fc00000);
+        if (loss_out) { loss_out[0] = qnan; loss_out[1] = qnan; loss_out[2] = qnan; }
+        if (acc) { acc[0] = qnan; acc[1] = qnan; acc[2] = qnan; }
+    }
 }
 
 static int key_bits(int n_items) {
@@ -136,8 +145,10 @@ int hvae_batch_transpose(const int64_t* indptr, const int32_t* indices, const fl
     return 0;
 }
 
-int hvae_batch_release(const int32_t* uniq_item, const int32_t* n_unique, int cap, int32_t* slot_of_item, void* stream) {
-    launch_pdl(batch_release_kernel, ceil_div(cap, 256), 256, 0, (cudaStream_t)stream, uniq_item, n_unique, cap, slot_of_item);
+int hvae_batch_release(const int32_t* uniq_item, const int32_t* n_unique, int cap, int32_t* slot_of_item, const int32_t* overflow,
+                       float* loss_out, float* acc, void* stream) {
+    launch_pdl(batch_release_kernel, ceil_div(cap, 256), 256, 0, (cudaStream_t)stream, uniq_item, n_unique, cap, slot_of_item, overflow,
+               loss_out, acc);
     HVAE_LAUNCH_CHECK("batch_release");
     return 0;
 }

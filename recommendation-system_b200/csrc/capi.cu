@@ -22,7 +22,7 @@ bool hvae::pdl_enabled() {
 }
 
 extern "C" const char* hvae_last_error(void) { return g_err; }
-extern "C" int hvae_abi_version(void) { return 1; }
+extern "C" int hvae_abi_version(void) { return 2; }
 
 // ---- host <-> device plumbing of the per-step API (VAETrainer.train_on_batch) --------------------------------------
 // The batch's CSR slice from (pinned) host memory into the step's static device buffers as three async copies behind one

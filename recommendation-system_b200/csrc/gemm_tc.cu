@@ -90,7 +90,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 
 __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB, TGemmParams P) {
-    pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int TG_STAGES = P.n_stages, TG_STAGE = P.stage_bytes;
@@ -117,6 +116,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    // "dependents may launch" only now that this CTA holds its TMEM columns: a dependent tensor-core kernel that landed on this
+    // SM earlier could take the columns and then park in griddepcontrol.wait on us while we block in tcgen05.alloc
+    pdl_launch_dependents();
     pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
 
     if (warp == 0) {

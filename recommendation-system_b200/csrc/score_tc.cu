@@ -63,7 +63,6 @@ __device__ __forceinline__ bool better(float v, int i, float tv, int ti) { retur
 template <int MODE>
 __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_constant__ CUtensorMap tmU,
                                                              const __grid_constant__ CUtensorMap tmE, StatsParams P) {
-    pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + STAGES * STAGE_BYTES);
@@ -88,6 +87,9 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    // "dependents may launch" only now that this CTA holds its TMEM columns: a dependent tensor-core kernel that landed on this
+    // SM earlier could take the columns and then park in griddepcontrol.wait on us while we block in tcgen05.alloc
+    pdl_launch_dependents();
     pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
 
     if (warp == 0) {
@@ -338,6 +340,7 @@ struct GradParams {
     // one-pass mode (c_part != null)
     float* c_part;        // [n_splits][B]  shift the split ended up with
     float* l_part;        // [n_splits][n_sub][B]  row sums of the numerators (n_sub = 2 for the pair kernel: one per CTA)
+    int box3d;            // cta_group::2 kernel: the tensor maps are the 3-D (64 columns, rows, 64-column blocks) views
 };
 
 // Softmax numerators of one [128 users x 128 items] score tile, thread <-> user row: p = exp2(v * log2e - shift2), packed to
@@ -389,7 +392,6 @@ __device__ __forceinline__ float merged_lse(const float* part_m, const float* pa
 
 __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constant__ CUtensorMap tmU,
                                                             const __grid_constant__ CUtensorMap tmE, GradParams P) {
-    pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* pbuf = smem + G_STAGES * G_SLOT;                         // 2 x 32 KB
@@ -419,6 +421,9 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    // "dependents may launch" only now that this CTA holds its TMEM columns: a dependent tensor-core kernel that landed on this
+    // SM earlier could take the columns and then park in griddepcontrol.wait on us while we block in tcgen05.alloc
+    pdl_launch_dependents();
     pdl_wait();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
     const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
     const bool onepass = P.c_part != nullptr;
@@ -598,7 +603,6 @@ __global__ void __launch_bounds__(192, 1) score_grad_kernel(const __grid_constan
 // uses per sweep.
 __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_constant__ CUtensorMap tmU,
                                                                  const __grid_constant__ CUtensorMap tmE, GradParams P) {
-    pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* pbuf = smem + G_STAGES * G_SLOT;                         // 2 x 32 KB
@@ -630,6 +634,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
     cluster_sync_all();            // the peer's barriers are initialised before anybody arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_launch_dependents();       // after the TMEM allocation (see score_stats_kernel)
     pdl_wait();
     const uint32_t tmem_O = tmem_base, tmem_S = tmem_base + G_DCHUNK;
     auto own = [&](int ti) { return (uint32_t)(ti & 1) == rank; };
@@ -817,6 +822,8 @@ __global__ void __launch_bounds__(192, 1) score_grad_pair_kernel(const __grid_co
 
 constexpr size_t kGradSmem = G_STAGES * G_SLOT + 2 * G_PBYTES + 1536 + 1024;
 
+#include "score_duo.cuh"
+
 // Item splits per (user tile, column chunk): one CTA per SM in a single wave when each CTA would otherwise get only a
 // few tiles (the prologue -- barrier init, TMEM alloc, first TMA -- costs about one tile), two waves for long CTAs.
 static int pick_wave_splits(int units, int n_tiles) {
@@ -865,6 +872,23 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int l
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return hvae_fail("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return 0;
+}
+
+// The same matrix (needs cols % 64 == 0) seen as (64 columns, rows, cols / 64 column blocks): box = [2 blocks][64 rows][64 columns],
+// i.e. two consecutive [64 x 64] 128B-swizzled operand boxes per TMA instruction.
+int make_tmap_bf16_blocks(CUtensorMap* out, const void* base, int rows, int cols, int ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return hvae_fail("cuTensorMapEncodeTiled is not available from the driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 || cols % 64) return hvae_fail("blocked TMA view needs cols %% 64 == 0 (cols=%d ld=%d)", cols, ld);
+    cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
+    cuuint32_t box[3] = {64, 64, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return hvae_fail("cuTensorMapEncodeTiled (blocked view) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
     return 0;
 }
 
@@ -921,45 +945,67 @@ static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int ld
     return 0;
 }
 
-static bool grad_is_pair(int d) {
+// Which kernel runs the two chained GEMMs: the CTA-pair kernel (tcgen05 cta_group::2, score_duo.cuh) for d <= 768, the
+// DSMEM pair of column-chunk CTAs for 384 < d <= 768 when the former is disabled, the one-CTA-per-chunk kernel otherwise.
+// HVAE_SCORE_KERNEL = duo | pair | single overrides (profiling / A-B runs).
+enum GradKind { GRAD_SINGLE = 0, GRAD_PAIR = 1, GRAD_DUO = 2 };
+static long long* g_duo_trace = nullptr;     // hvae_tc_duo_trace (profiling)
+static GradKind grad_kind(int d) {
+    static const char* env = getenv("HVAE_SCORE_KERNEL");
     static const bool no_pair = getenv("HVAE_NO_PAIR") != nullptr;
-    return ceil_div(round_up(d, BK), G_DCHUNK) == 2 && !no_pair;
+    const bool two_chunks = ceil_div(round_up(d, BK), G_DCHUNK) == 2;
+    if (env && env[0] == 's') return GRAD_SINGLE;
+    if (env && env[0] == 'p') return two_chunks && !no_pair ? GRAD_PAIR : GRAD_SINGLE;
+    if (d <= D_MAXD) return GRAD_DUO;
+    return two_chunks && !no_pair ? GRAD_PAIR : GRAD_SINGLE;
 }
+static int grad_units_per_mtile(int d) { return grad_kind(d) == GRAD_DUO ? 2 : ceil_div(round_up(d, BK), G_DCHUNK); }
 
 static int launch_grad(const void* U, int ldu, int B, const void* E, int lde, int N, int d, const float* lse, const float* part_m,
                        const float* part_l, int lse_splits, float* lse_out, float* Opart, int ldo, cudaStream_t stream,
                        float* c_part = nullptr, float* l_part = nullptr) {
     HVAE_REQUIRE(ldo % 4 == 0 && ldo >= d, "tc_score_grad: bad ldo=%d for d=%d", ldo, d);
+    const GradKind kind = grad_kind(d);
     CUtensorMap tmU, tmE;
-    if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, BM)) return rc;
-    if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, 64)) return rc;
+    static const bool no3d = getenv("HVAE_DUO_NO3D") != nullptr;
+    const bool box3d = kind == GRAD_DUO && d % 64 == 0 && !no3d && make_tmap_bf16_blocks(&tmU, U, B, d, ldu) == 0 &&
+                       make_tmap_bf16_blocks(&tmE, E, N, d, lde) == 0;
+    if (!box3d) {
+        if (int rc = make_tmap_bf16(&tmU, U, B, d, ldu, kind == GRAD_DUO ? 64 : BM)) return rc;
+        if (int rc = make_tmap_bf16(&tmE, E, N, d, lde, 64)) return rc;
+    }
     const int m_tiles = ceil_div(B, BM), n_chunks = ceil_div(round_up(d, BK), G_DCHUNK), n_tiles = ceil_div(N, G_BN);
     GradParams P{};
     P.B = B; P.N = N; P.d = d; P.lse = lse; P.part_m = part_m; P.part_l = part_l; P.lse_splits = lse_splits; P.lse_out = lse_out;
     P.Opart = Opart; P.ldo = ldo;
-    P.c_part = c_part; P.l_part = l_part;
-    P.n_splits = pick_grad_splits(m_tiles, n_chunks, n_tiles);
+    P.c_part = c_part; P.l_part = l_part; P.box3d = box3d ? 1 : 0;
+    P.n_splits = pick_grad_splits(m_tiles, grad_units_per_mtile(d), n_tiles);
     P.tiles_per_split = ceil_div(n_tiles, P.n_splits);
     static bool attr_set = false;
     if (!attr_set) {
         HVAE_CUDA(cudaFuncSetAttribute(score_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
         HVAE_CUDA(cudaFuncSetAttribute(score_grad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_grad_duo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDuoSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_grad_duo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDuoSmem));
         attr_set = true;
     }
-    if (n_chunks == 2 && grad_is_pair(d)) {      // the two column-chunk CTAs share the softmax tiles through DSMEM (cluster of 2 along y)
+    if (kind != GRAD_SINGLE) {      // clusters of 2 along y: the CTA pair of one (user tile, item range)
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(m_tiles, 2, P.n_splits);
+        // (the CTA pair of a cta_group::2 kernel must lie along x; the DSMEM pair kernel keeps its (user tile, chunk) grid)
+        cfg.gridDim = kind == GRAD_DUO ? dim3(2, m_tiles, P.n_splits) : dim3(m_tiles, 2, P.n_splits);
         cfg.blockDim = dim3(192);
-        cfg.dynamicSmemBytes = kGradSmem;
+        cfg.dynamicSmemBytes = kind == GRAD_DUO ? kDuoSmem : kGradSmem;
         cfg.stream = stream;
         cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = kind == GRAD_DUO ? 2 : 1; attr[0].val.clusterDim.y = kind == GRAD_DUO ? 1 : 2; attr[0].val.clusterDim.z = 1;
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        HVAE_CUDA(cudaLaunchKernelEx(&cfg, score_grad_pair_kernel, tmU, tmE, P));
+        if (kind == GRAD_DUO && g_duo_trace) HVAE_CUDA(cudaLaunchKernelEx(&cfg, score_grad_duo_kernel<true>, tmU, tmE, P, g_duo_trace));
+        else if (kind == GRAD_DUO) HVAE_CUDA(cudaLaunchKernelEx(&cfg, score_grad_duo_kernel<false>, tmU, tmE, P, (long long*)nullptr));
+        else HVAE_CUDA(cudaLaunchKernelEx(&cfg, score_grad_pair_kernel, tmU, tmE, P));
         HVAE_LAUNCH_CHECK("tc_score_grad(pair)");
         return 0;
     }
@@ -1017,7 +1063,7 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
 
 
 // 1 or 2 numerator sums per (split, row): the pair kernel's two CTAs each report the tiles they owned
-size_t hvae_tc_onepass_subparts(int d) { return grad_is_pair(d) ? 2 : 1; }
+size_t hvae_tc_onepass_subparts(int d) { return grad_kind(d) != GRAD_SINGLE ? 2 : 1; }
 
 // Forward and backward through the scores in ONE sweep over the items (4 B N d executed flops instead of the 6 B N d of
 // hvae_tc_score_lse_grad): the backward kernel takes the softmax numerators against a score-independent shift and also returns
@@ -1039,8 +1085,43 @@ int hvae_tc_onepass_combine(const float* c_part, const float* l_part, int n_part
     return 0;
 }
 
+// Profiling: while `trace` is non-null the cta_group::2 scoring kernel runs its instrumented build and writes, per CTA and per
+// role (0 TMA producer, 1 MMA issuer, 2 first softmax warp), 8 int64 cycle counters: [wait0..wait3, -, -, -, lifetime]
+// (producer: wait0 = ring slot free; MMA: S buffer free, G1 operands, P written, G2 operands; softmax: S ready, P buffer free,
+// sweep's MMAs done).  trace: [n_splits * m_tiles * 2][3][8] int64 device memory.
+int hvae_tc_duo_trace(int64_t* trace_) {
+    long long* trace = reinterpret_cast<long long*>(trace_);
+    g_duo_trace = trace;
+    return 0;
+}
+
+// Diagnostic: how many CTA pairs of the cta_group::2 scoring kernel the device can hold at once with `smem_bytes` of dynamic
+// shared memory per CTA (0 = the kernel's own size); negative = the query failed (hvae_last_error()).
+int hvae_tc_duo_max_clusters(int smem_bytes) {
+    const size_t smem = smem_bytes > 0 ? (size_t)smem_bytes : kDuoSmem;
+    if (cudaFuncSetAttribute(score_grad_duo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        hvae_fail("tc_duo_max_clusters: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2, 1, 74);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, score_grad_duo_kernel<false>, &cfg) != cudaSuccess) {
+        hvae_fail("tc_duo_max_clusters: %s", cudaGetErrorString(cudaGetLastError()));
+        return -2;
+    }
+    return n;
+}
+
 size_t hvae_tc_grad_splits(int B, int N, int d) {
-    return (size_t)pick_grad_splits(ceil_div(B, BM), ceil_div(round_up(d, BK), G_DCHUNK), ceil_div(N, G_BN));
+    return (size_t)pick_grad_splits(ceil_div(B, BM), grad_units_per_mtile(d), ceil_div(N, G_BN));
 }
 
 // Opart: [hvae_tc_grad_splits(B,N,d)][B][ldo] floats, ldo % 4 == 0, ldo >= d; every partial is fully written for

@@ -97,8 +97,10 @@ class DataParallel:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         # gradient exchange: "nvl" = our one-shot all-gather by direct (multicast) stores into symmetric memory,
-        # "nccl" = NCCL all-gather.  "auto" tries nvl and falls back to nccl if symmetric memory cannot be set up.
+        # "nccl" = NCCL all-gather.  "auto" = nvl if symmetric memory can be set up on EVERY rank (decided once,
+        # collectively, in prepare_exchange -- never inside a step), else nccl.
         self.exchange_mode = os.environ.get("HVAE_DP_EXCHANGE", "auto")
+        self.exchange = None          # "nvl" | "nccl" once decided
         self._sym = None
 
     # -- batch splitting -------------------------------------------------------------------------------------
@@ -158,7 +160,10 @@ class DataParallel:
         send_rows[:B].copy_(rows)
         rows_all = eng.ws.get("dp_rows_all", (self.world * bm,), torch.int32)
         dist.all_gather_into_tensor(rows_all, send_rows, group=self.group)
-        cap = batch.nnz_cap_global if getattr(batch, "nnz_cap_global", None) else batch.nnz_cap * self.world
+        cap = getattr(batch, "nnz_cap_global", None)
+        if not cap:     # world * local bound is NOT a bound when other ranks hold denser users: insist on the real one
+            raise RuntimeError("data-parallel steps need Batch.nnz_cap_global (an upper bound of the GLOBAL batch's nnz); "
+                               "ShardedCSRLoader and VAETrainer.train_on_batch provide it")
         return Batch(batch.csr, rows_all, rows_all.shape[0], cap)
 
     def _symmetric(self, eng, n_floats):
@@ -173,14 +178,38 @@ class DataParallel:
         eng.ws.generation += 1          # captured graphs must not keep pointers into an older buffer
         return self._sym
 
+    def prepare_exchange(self, eng, n_floats):
+        """Decide the gradient-exchange path ONCE and on all ranks together: try to set up the symmetric receive buffer,
+        all-reduce a success flag, and fall back to NCCL only if some rank could not (a set-up error, never a step error;
+        a rank falling back alone would leave the others in the symmetric-memory barrier)."""
+        if self.exchange is not None and (self.exchange == "nccl" or (self._sym is not None and self._sym["n"] >= n_floats)):
+            return self.exchange
+        if self.exchange_mode == "nccl":
+            self.exchange = "nccl"
+            return self.exchange
+        ok, err = 1, None
+        try:
+            self._symmetric(eng, n_floats)
+        except Exception as e:          # set-up only (symmetric-memory allocation / rendezvous); reported below
+            ok, err = 0, e
+        flag = torch.tensor([ok], dtype=torch.int32, device=eng.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self.exchange = "nvl"
+        elif self.exchange_mode == "nvl":
+            raise RuntimeError(f"HVAE_DP_EXCHANGE=nvl but symmetric memory is unavailable on some rank: {err}")
+        else:
+            self.exchange, self._sym = "nccl", None
+        return self.exchange
+
     def exchange_grads(self, eng, batch, dpre0):
-        if self.exchange_mode in ("auto", "nvl"):
-            try:
-                return self._exchange_grads_nvl(eng, batch, dpre0)
-            except Exception:
-                if self.exchange_mode == "nvl":
-                    raise
-                self.exchange_mode = "nccl"
+        n = self.world * (eng.gd.numel() + self.b_max(eng.b_global) * dpre0.shape[1])
+        if self.exchange is None or (self.exchange == "nvl" and self._sym["n"] < n):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the gradient exchange must be set up before graph capture (run one eager step first)")
+            self.prepare_exchange(eng, n)
+        if self.exchange == "nvl":
+            return self._exchange_grads_nvl(eng, batch, dpre0)
         return self._exchange_grads_nccl(eng, batch, dpre0)
 
     def _exchange_grads_nvl(self, eng, batch, dpre0):

@@ -543,7 +543,7 @@ class Engine:
         multi_slot = ws.get("w1_multi_slot", (int(lib.w1_max_partial_rows(cap)),), i32)
         n_work = ws.get("w1_n_work", (2,), i32, zero=True)
         lib.w1_plan(p(seg_start), p(n_unique), cap, p(chunk_base), p(part_base), p(work_slot), p(multi_slot), p(n_work), st)
-        return dict(cap=cap, seg_start=seg_start, n_unique=n_unique, eid_sorted=arr["eid_sorted"], ent_user=arr["ent_user"],
+        return dict(cap=cap, overflow=overflow, seg_start=seg_start, n_unique=n_unique, eid_sorted=arr["eid_sorted"], ent_user=arr["ent_user"],
                     ent_val=ent_val, uniq=arr["uniq_item"], chunk_base=chunk_base, part_base=part_base, work_slot=work_slot,
                     multi_slot=multi_slot, n_work=n_work)
 
@@ -596,7 +596,19 @@ class Engine:
         with self.span("adam"):
             lib.adam_step(p(self.arena), p(self.m), p(self.v), lay.n_params, lay.n_w1, r4(lay.hidden[0]), p(self.slot_of_item), p(gs),
                           p(self.gd), p(self.state), weight_decay, self.ADAM_B1, self.ADAM_B2, self.ADAM_EPS, st)
-        lib.batch_release(p(uniq), p(n_unique), wbatch.nnz_cap, p(self.slot_of_item), st)
+        # restores slot_of_item; a batch that did not fit its nnz bound turns the step's loss into NaN (see check_overflow)
+        lib.batch_release(p(uniq), p(n_unique), wbatch.nnz_cap, p(self.slot_of_item), p(tb["overflow"]), p(self.loss_out), p(self.acc), st)
+
+    def check_overflow(self):
+        """Raise if a training step since the last call dropped batch rows because its nnz bound (Batch.nnz_cap /
+        nnz_cap_global) was too small -- such a step has an incomplete layer-1 weight gradient.  Called by the trainer
+        whenever it reads a NaN loss back (the kernels poison the loss of such a step), so it costs nothing per step."""
+        ov = self.ws.buf.get("bt_overflow")
+        if ov is not None and int(ov[0].item()) != 0:
+            n = int(ov[0].item())
+            ov.zero_()
+            raise RuntimeError(f"hvae_b200: {n} batch row(s) did not fit the batch's nnz bound (Batch.nnz_cap / nnz_cap_global too "
+                               "small): the layer-1 weight gradient of that step was incomplete; pass an exact bound")
 
     def eval_step(self, batch: Batch, beta, b_global=None):
         """Validation forward: eval mode (z = mu, no dropout), fixed beta (src/ml/train.py:105-117)."""

@@ -70,8 +70,10 @@ class CSRLoader:
 
     def __iter__(self):
         n = len(self.user_indices)
+        # every DataLoader iterator -- shuffled or not -- draws its _base_seed from the global CPU generator
+        # (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__): the validation loader advances the stream too
+        torch.empty((), dtype=torch.int64).random_()
         if self.shuffle:
-            torch.empty((), dtype=torch.int64).random_()        # DataLoader iterator's _base_seed draw
             seed = int(torch.empty((), dtype=torch.int64).random_().item())   # RandomSampler's seed draw
             g = torch.Generator()
             g.manual_seed(seed)
@@ -369,6 +371,7 @@ class VAETrainer:
                 nnz_cap_global = int(t.item()) * dp.world
             return Batch(csr, rows_d, x.shape[0], max(1, cap), b_global=b_global, nnz_cap_global=nnz_cap_global)
         if isinstance(x, torch.Tensor) and x.layout == torch.sparse_csr:
+            self._check_host_csr(x)
             crow, col, val = x.crow_indices(), x.col_indices(), x.values()
             nnz = int(col.shape[0])
             dev = self.device
@@ -379,8 +382,23 @@ class VAETrainer:
             return Batch(csr, None, x.shape[0], max(1, nnz))
         return self.model._as_batch(x.to(self.device, non_blocking=True))
 
+    def _check_host_csr(self, x):
+        """Shape / structure checks of a caller-supplied CSR batch before it reaches the kernels (an out-of-range column
+        would index W1^T and slot_of_item out of bounds).  Host batches only: a few KB, microseconds."""
+        crow, col = x.crow_indices(), x.col_indices()
+        if x.dim() != 2 or x.shape[1] != self.model.n_items:
+            raise ValueError(f"expected a [B, {self.model.n_items}] batch, got {tuple(x.shape)}")
+        if crow.is_cuda:
+            return
+        nnz = int(col.shape[0])
+        if crow.shape[0] != x.shape[0] + 1 or int(crow[0]) != 0 or int(crow[-1]) != nnz:
+            raise ValueError("malformed CSR batch: crow_indices must run from 0 to nnz over B+1 entries")
+        if nnz and (int(col.min()) < 0 or int(col.max()) >= self.model.n_items):
+            raise ValueError(f"CSR batch has column indices outside [0, {self.model.n_items})")
+
     def _host_csr_step(self, x, b_global):
         """Host CSR batch -> static device buffers (one H2D copy per array) -> replay of the captured step."""
+        self._check_host_csr(x)
         crow, col, val = x.crow_indices(), x.col_indices(), x.values()
         nnz, B = int(col.shape[0]), x.shape[0]
         ent = self._graph_entry("csr", Batch(None, None, B, max(1, nnz)), b_global)
@@ -424,6 +442,8 @@ class VAETrainer:
         if eng.dist is not None:
             eng.dist.reduce_losses(eng.acc)
         acc = eng.acc.cpu().numpy().astype(np.float64)     # the epoch's only device->host read
+        if np.isnan(acc[0]):
+            eng.check_overflow()
         n = max(1.0, acc[3])
         return {"total_loss": float(acc[0] / n), "recon_loss": float(acc[1] / n), "kl_loss": float(acc[2] / n)}
 
@@ -445,7 +465,10 @@ class VAETrainer:
         if self._loss_host is None:
             self._loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
         eng.lib.d2h_floats(p(eng.loss_out), 3, self._loss_host.data_ptr(), eng.stream)
-        return tuple(self._loss_host.tolist())
+        out = tuple(self._loss_host.tolist())
+        if out[0] != out[0]:          # NaN: either a genuine one or a step whose batch overflowed its nnz bound
+            eng.check_overflow()
+        return out
 
     def save_checkpoint(self, path, epoch: int, is_best: bool = False, extra: dict | None = None) -> None:
         """src/ml/train.py:126-145: same keys; tensors in the reference's shapes."""

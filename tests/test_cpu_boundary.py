@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     dll = ctypes.CDLL(str(_cabi.LIB_PATH))
     for name in decls:
         assert hasattr(dll, name), name
-    assert _cabi.lib().abi_version() == 1
+    assert _cabi.lib().abi_version() == 2
     assert ctypes.sizeof(_cabi.StepState) == 48
 
 
@@ -123,6 +123,32 @@ def test_csr_loader_matches_dataloader_order():
         dense = torch.from_numpy(np.asarray(m[ob.rows.numpy()].toarray(), dtype=np.float32))
         assert torch.equal(dense, rb)
         assert ob.nnz_cap >= int((dense != 0).sum())
+
+
+def test_csr_loader_multi_epoch_train_validate_order():
+    """Three epochs of train (shuffled) + validate (not shuffled): every DataLoader iterator -- the validation one too --
+    draws a _base_seed from the global generator, so from epoch 2 on the permutations only match if CSRLoader draws it as well."""
+    from scipy.sparse import random as sprand
+    from hvae_b200.train import CSRLoader, UserInteractionDataset
+    m = sprand(50, 30, density=0.2, format="csr", random_state=1)
+    tr_users, va_users = list(range(0, 41)), list(range(5, 33))
+    torch.manual_seed(11)
+    ref_tr = torch.utils.data.DataLoader(UserInteractionDataset(m, tr_users), batch_size=16, shuffle=True)
+    ref_va = torch.utils.data.DataLoader(UserInteractionDataset(m, va_users), batch_size=16, shuffle=False)
+    ref = []
+    for _ in range(3):
+        ref.append([b.clone() for b in ref_tr])
+        ref.append([b.clone() for b in ref_va])
+    torch.manual_seed(11)
+    tr, va = CSRLoader(m, tr_users, 16, True, device="cpu"), CSRLoader(m, va_users, 16, False, device="cpu")
+    ours = []
+    for _ in range(3):
+        ours.append(list(tr))
+        ours.append(list(va))
+    for o_ep, r_ep in zip(ours, ref):
+        assert len(o_ep) == len(r_ep)
+        for ob, rb in zip(o_ep, r_ep):
+            assert torch.equal(torch.from_numpy(np.asarray(m[ob.rows.numpy()].toarray(), dtype=np.float32)), rb)
 
 
 def test_metric_functions_match_oracle():
