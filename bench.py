@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""Benchmark of the HybridVAE hot path (BASELINE.json metric: train users/sec & eval top-K users/sec).
+"""Benchmark of the HybridVAE hot path (BASELINE.json metric: train users/sec & eval top-K users/sec; % of TC/HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--precision bf16|fp32]
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
 
-A "step" is one optimisation step (forward, multinomial-NLL + KL, backward, clip, Adam) over one batch of
-synthetic users of the named workload (hvae_b200.synth.CONFIGS, shapes from BASELINE.json `configs`).
-Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how each field is obtained.
+Default workload = BASELINE.json configs[2] (C3): 1M users x 200k items, d = 768, 4,096 users per GPU and step -- the
+largest single-GPU configuration and the one the 1/2/4/8-GPU scaling is quoted on.  A "step" is one optimisation step
+(forward, multinomial NLL + KL, backward, clip, Adam) over one batch of synthetic users.  Rank 0 prints ONE JSON line;
+besides the contract's keys it carries `extra`: the C2 training step, a C4-shape (1M items) evaluation -- item-sharded over
+the ranks when N > 1 --, kernel rooflines at the 1M-item shape, the gradient-exchange path and a data-parallel parity number.
+See DESIGN.md §6 for how each field is obtained.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -28,20 +32,23 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC, UNIT = "train_users_per_sec", "users/s"
+DESC = {"c1": "Appliances-shaped synthetic", "c2": "All_Beauty-shaped synthetic", "c3": "1M users x 200k items synthetic"}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3"])
     ap.add_argument("--precision", default=os.environ.get("HVAE_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="users per GPU per step (default: the workload's)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU-baseline sample (b200 arm)")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="budget of the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     return ap.parse_args()
 
@@ -64,7 +71,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.samples, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -108,72 +115,508 @@ def make_workload(name, batch_override=0):
     return c, data, E
 
 
-def cpu_reference_run(c, data, E, steps, warmup, seconds=None):
-    """The reference's train_epoch arithmetic on the host cores (oracle port; src/ml/train.py:81-103): DataLoader row
-    densification, dense fp32 forward/backward through ATen, clip, Adam.  Returns users/s over `steps` steps (or as many
-    as fit in `seconds`), after `warmup` untimed ones."""
-    from oracle import hvae_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    m = orc.OracleVAE(c["n_items"], E, c["latent_dim"], c["hidden_dims"], c["dropout"], c["beta"])
-    csr = data.scipy_csr()
-    B = c["batch"]
-    rng = np.random.default_rng(0)
-    order = rng.permutation(c["n_users"])
-    opt = orc.make_adam(m)
-    m.train()
-    done, t_used, s = 0, 0.0, 0
-    total_steps = warmup + steps
-    while s < total_steps:
-        rows = order[(s * B) % c["n_users"]:][:B]
-        if len(rows) < B:
-            rows = order[:B]
+def workload_config(name, c, n_gpus):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": f"{name}: {DESC[name]} ({c['n_users']} users x {c['n_items']} items, d={c['emb_dim']}, latent {c['latent_dim']}, "
+                        f"hidden {c['hidden_dims']}), HybridVAE training step",
+            "users_per_gpu_per_step": c["batch"], "global_batch": c["batch"] * n_gpus,
+            "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
+            "l2": "working set (W1 + Adam moments + E) exceeds L2 at c3; in addition a 256 MiB write flushes L2 between timed steps (untimed)"}
+
+
+# ---- the reference's arithmetic on the host cores (oracle port) ------------------------------------------------------
+class CpuReference:
+    """The reference's train_epoch arithmetic (src/ml/train.py:81-103): DataLoader row densification, dense fp32 forward /
+    backward through ATen, clip_grad_norm_(5), Adam -- oracle/hvae_oracle.py, all host threads.  `step(B_s)` runs one
+    optimisation step over B_s users of the workload (a bounded sample of the 4,096-user batch when the full one would not fit
+    the time budget: at c3 a full step is ~6 TFLOP of dense fp32 GEMM + a 3.3 GB dense batch)."""
+
+    def __init__(self, c, data, E):
+        from oracle import hvae_oracle as orc
+        self.orc, self.c = orc, c
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        self.m = orc.OracleVAE(c["n_items"], E, c["latent_dim"], c["hidden_dims"], c["dropout"], c["beta"])
+        self.opt = orc.make_adam(self.m)
+        self.m.train()
+        self.csr = data.scipy_csr()
+        self.order = np.random.default_rng(0).permutation(c["n_users"])
+        self.pos = 0
+        self.threads = torch.get_num_threads()
+
+    def step(self, B):
+        c, orc = self.c, self.orc
+        if self.pos + B > len(self.order):
+            self.pos = 0
+        rows = self.order[self.pos:self.pos + B]
+        self.pos += B
         t0 = time.perf_counter()
-        x = torch.stack([torch.FloatTensor(csr[int(r)].toarray().flatten()) for r in rows])   # train.py:45-47 + default collate
-        opt.zero_grad()
-        sc, mu, lv = m.forward_ref(x)
+        x = torch.stack([torch.FloatTensor(self.csr[int(r)].toarray().flatten()) for r in rows])   # train.py:45-47 + default collate
+        self.opt.zero_grad()
+        sc, mu, lv = self.m.forward_ref(x)
         loss, _, _ = orc.loss_terms(sc, x, mu, lv, c["beta"])
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=5.0)
-        opt.step()
+        torch.nn.utils.clip_grad_norm_(self.m.parameters(), max_norm=5.0)
+        self.opt.step()
         loss.item()
-        dt = time.perf_counter() - t0
-        if s >= warmup:
-            done += len(rows)
-            t_used += dt
-            if seconds is not None and t_used >= seconds and s - warmup + 1 >= 4:
-                s += 1
-                break
-        s += 1
-    n_steps = s - warmup
-    return done / t_used, n_steps, t_used, torch.get_num_threads()
+        return time.perf_counter() - t0
+
+    def pick_sample(self, seconds_per_step, B_full):
+        """Largest power-of-two-ish sample <= the full batch whose step fits `seconds_per_step` (probe at 128 users; a step's
+        cost is affine in the sample size, so the linear extrapolation is conservative)."""
+        probe = min(B_full, 128)
+        t = self.step(probe)
+        t = min(t, self.step(probe))
+        B = int(probe * max(1.0, 0.8 * seconds_per_step / t))
+        B = min(B_full, max(probe, 1 << (B.bit_length() - 1)))
+        return B
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     c, data, E = make_workload(args.workload, args.batch)
-    steps = min(args.steps, 60)          # each CPU step is ~0.1-0.2 s at C2; keep the run within a few minutes
-    ups, n_steps, secs, cores = cpu_reference_run(c, data, E, steps, min(args.warmup, 3))
-    line = {"impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": n_steps,
-            "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * secs / n_steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, c, 1, "cpu"),
-            "cpu_baseline": {"value": ups, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{n_steps} steps of batch {c['batch']} ({n_steps * c['batch']} users), "
-                                       "oracle/hvae_oracle.py train loop incl. row densification"},
-            "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    ref = CpuReference(c, data, E)
+    W, K = args.warmup, args.steps
+    Bs = ref.pick_sample(args.ref_seconds / max(1, W + K), c["batch"])
+    for _ in range(W):
+        ref.step(Bs)
+    secs = sum(ref.step(Bs) for _ in range(K))
+    ups = K * Bs / secs
+    sample = (f"{K} steps of {Bs} users each (a bounded sample of the {c['batch']}-user batch of the same workload; users/s = sample users / "
+              f"step time), oracle/hvae_oracle.py = the reference's train loop incl. row densification, {ref.threads} host threads")
+    line = {"impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.workload, c, args.gpus),
+            "cpu_baseline": {"value": ups, "unit": UNIT, "cores": ref.threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "sample_users_per_step": Bs}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, c, n_gpus, precision):
-    desc = {"c1": "Appliances-shaped synthetic", "c2": "All_Beauty-shaped synthetic", "c3": "1M users x 200k items synthetic"}[name]
-    return {"workload": f"{name}: {desc} ({c['n_users']} users x {c['n_items']} items, d={c['emb_dim']}, latent {c['latent_dim']}, "
-                        f"hidden {c['hidden_dims']}), HybridVAE training step",
-            "users_per_gpu_per_step": c["batch"], "global_batch": c["batch"] * n_gpus, "precision": precision,
-            "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
-            "l2": "L2 flushed (256 MiB write) between timed steps, untimed"}
+# ---- helpers of the b200 arm -------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def dist_max(vals, dev, world):
+    if world == 1:
+        return [float(v) for v in vals]
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def barrier(dev, world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+
+def timed_events(fn, n, flush_buf, dev):
+    """n calls of fn(i), each bracketed by CUDA events on the current stream, L2 flushed (untimed) before each -> ms list."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for i in range(n):
+        if flush_buf is not None:
+            flush_buf.fill_(i & 0xFF)
+        evs[i][0].record()
+        fn(i)
+        evs[i][1].record()
+    torch.cuda.synchronize(dev)
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def build_train(name, args, dev, world, rank, batch_override=0):
+    """Model + trainer + resident CSR + the walk over global batches of one workload."""
+    from hvae_b200.engine import Batch, DeviceCSR
+    from hvae_b200.model import HybridVAE
+    from hvae_b200.train import VAETrainer
+    x = Ctx()
+    x.name = name
+    x.c, x.data, x.E = make_workload(name, batch_override)
+    c = x.c
+    x.B, x.U, x.N, x.d = c["batch"], c["n_users"], c["n_items"], c["emb_dim"]
+    torch.manual_seed(0)
+    x.model = HybridVAE(x.N, x.E, c["latent_dim"], c["hidden_dims"], c["dropout"], c["beta"], precision=args.precision)
+    x.trainer = VAETrainer(x.model, dev, lr=1e-3, use_cuda_graph=not args.no_graph)
+    x.dp = x.trainer.enable_data_parallel() if world > 1 else None
+    x.csr = DeviceCSR.from_arrays(x.data.indptr, x.data.indices, None, x.N, dev)
+    x.Bg = x.B * world
+    order = np.random.default_rng(0).permutation(x.U).astype(np.int32)
+    x.order = np.concatenate([order, order[:x.Bg]])
+    x.order_dev = torch.from_numpy(x.order).to(dev)
+    x.lens = np.diff(x.data.indptr)
+    x.n_batches = max(1, x.U // x.Bg)
+    x.cap_local = max(int(x.lens[x.order[i * x.Bg + rank * x.B:i * x.Bg + (rank + 1) * x.B]].sum()) for i in range(x.n_batches))
+    x.cap_global = max(int(x.lens[x.order[i * x.Bg:(i + 1) * x.Bg]].sum()) for i in range(x.n_batches))
+
+    def batch_at(s):
+        g0 = (s % x.n_batches) * x.Bg
+        return Batch(x.csr, x.order_dev[g0 + rank * x.B:g0 + (rank + 1) * x.B], x.B, max(1, x.cap_local), b_global=x.Bg,
+                     nnz_cap_global=x.cap_global)
+    x.batch_at = batch_at
+    x.step = lambda s: x.trainer.train_step(batch_at(s), b_global=x.Bg)
+    x.model.train()
+    return x
+
+
+def measure_train(x, W, K, dev, world, rank, flush_buf, lib):
+    """W warm-up steps, then K timed steps (per-step CUDA events, L2 flushed in between) and K back-to-back steps."""
+    for s in range(W):
+        x.step(s)
+    barrier(dev, world)
+    l0 = lib.launches
+    t0 = time.perf_counter()
+    ms = timed_events(lambda i: x.step(W + i), K, flush_buf, dev)
+    barrier(dev, world)
+    t1 = time.perf_counter()
+    launches = lib.launches - l0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(K):
+        x.step(W + K + s)
+    e1.record()
+    barrier(dev, world)
+    ms_total, ms_hot = dist_max([sum(ms), e0.elapsed_time(e1)], dev, world)
+    return dict(value=K * x.Bg / (ms_total * 1e-3), ms_per_step=ms_total / K, value_hot=K * x.Bg / (ms_hot * 1e-3), ms_hot=ms_hot / K,
+                launches=launches, wall=(t0, t1))
+
+
+def kernel_spans(x, W, K, flush_buf, pk, world, ms_per_step, args):
+    """Per-kernel-group durations: CUDA events around each group on its launching stream over un-graphed steps of the same
+    workload -> achieved bytes/flops against the measured peaks."""
+    eng, trainer, model = x.model.engine, x.trainer, x.model
+    graph = trainer.use_cuda_graph
+    trainer.use_cuda_graph = False
+    eng.prof = {}
+    PS = min(K, 30)
+    for s in range(PS):
+        flush_buf.fill_(1)
+        x.step(W + 2 * K + s)
+    spans = eng.span_ms()
+    eng.prof = None
+    trainer.use_cuda_graph = graph
+    span_avg = {k: float(np.mean(v)) for k, v in spans.items()}
+    lay = model.layout
+    B, N, d, h = x.B, x.N, x.d, x.c["hidden_dims"]
+    nb = min(4, x.n_batches)
+    n_unique_avg = float(np.mean([len(np.unique(np.concatenate([x.data.indices[x.data.indptr[u]:x.data.indptr[u + 1]]
+                                                               for u in x.order[i * x.Bg:(i + 1) * x.Bg]]))) for i in range(nb)]))
+    ld1 = (h[0] + 3) // 4 * 4
+    adam_bytes = 24.0 * lay.n_params + 4.0 * (lay.n_dense + n_unique_avg * ld1)
+    flops_fwd = 2.0 * B * N * d
+    kernels = {}
+
+    def add(name, ms, bound, amount, extra=None):
+        unit = "GB/s" if bound == "hbm" else "TFLOP/s"
+        scale = 1e9 if bound == "hbm" else 1e12
+        peak = pk["hbm"] if bound == "hbm" else pk["tc_sustained"]
+        k = {"ms": ms, "bound": bound, "achieved": amount / (ms * 1e-3) / scale, "peak": peak, "unit": unit,
+             ("algorithmic_bytes" if bound == "hbm" else "algorithmic_flops"): amount}
+        k["frac"] = k["achieved"] / peak
+        k["share_of_step"] = ms / ms_per_step
+        if extra:
+            k.update(extra)
+        kernels[name] = k
+
+    if "adam" in span_avg:
+        add("adam", span_avg["adam"], "hbm", adam_bytes)
+    if "score_fwd" in span_avg:
+        add("score_fwd", span_avg["score_fwd"], "tensor", flops_fwd)
+    if "score_bwd" in span_avg:
+        add("score_bwd", span_avg["score_bwd"], "tensor", flops_fwd)
+    if "score_onepass" in span_avg:     # forward + backward through the scores in one sweep: S = U E^T and O = P E, 2BNd each
+        add("score_onepass", span_avg["score_onepass"], "tensor", 2 * flops_fwd,
+            {"launches": "one-pass scoring kernel (tcgen05 cta_group::2 for d <= 768) + combine", "executed_flops": 2 * flops_fwd,
+             "frac_of_burst_peak": 2 * flops_fwd / (span_avg["score_onepass"] * 1e-3) / 1e12 / pk["tc_burst"]})
+    if "gather" in span_avg:
+        nnz_avg = float(x.lens[x.order[:x.Bg * nb]].sum()) / nb / world
+        add("gather", span_avg["gather"], "hbm", nnz_avg * (ld1 * 4 + 4) + B * (3 * ld1 * 4 + 16))
+    dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
+    roofline = None
+    if dom:
+        kd = kernels[dom]
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get(f"{x.name}:{args.precision}:{dom}")
+        roofline = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"],
+                    "frac": kd["frac"], "traffic": traffic, "peak_source": pk["source"] + (" sustained" if kd["bound"] == "tensor" else ""),
+                    "ms_per_launch": kd["ms"], "share_of_step": kd["share_of_step"],
+                    "how": "CUDA events around the kernel on its launching stream over un-graphed steps of the timed workload; share = "
+                           "ms_per_launch / ms_per_step of the captured step"}
+    return kernels, span_avg, roofline
+
+
+def measure_e2e(x, K, dev, world, rank, flush_buf):
+    """The public per-batch API with HOST (pinned) inputs: H2D of the batch and D2H of the loss inside every timed step."""
+    KE = min(K, 100)
+    host = []
+    if world == 1:      # the step's input is the batch's CSR slice (indptr, indices, values) in pinned host memory
+        for s in range(KE):
+            g0 = (s % x.n_batches) * x.Bg
+            rows_h = x.order[g0:g0 + x.B].astype(np.int64)
+            starts, ln = x.data.indptr[rows_h], x.lens[rows_h]
+            crow = np.zeros(x.B + 1, dtype=np.int64)
+            np.cumsum(ln, out=crow[1:])
+            take = np.repeat(starts - crow[:-1], ln) + np.arange(int(ln.sum()), dtype=np.int64)
+            col = x.data.indices[take].astype(np.int32)
+            host.append(torch.sparse_csr_tensor(torch.from_numpy(crow).pin_memory(), torch.from_numpy(col).pin_memory(),
+                                                torch.ones(col.shape[0], dtype=torch.float32).pin_memory(), size=(x.B, x.N),
+                                                check_invariants=False))
+        h2d = float(np.mean([t.crow_indices().numel() * 8 + t.col_indices().numel() * 4 + t.values().numel() * 4 for t in host]))
+        api = "VAETrainer.train_on_batch(pinned host CSR batch) -> loss floats"
+    else:               # data parallel: the interaction CSR is resident on every rank; the step's input is its user ids
+        x.trainer.set_interactions(x.csr)
+        for s in range(KE):
+            g0 = (s % x.n_batches) * x.Bg
+            host.append(torch.from_numpy(x.order[g0 + rank * x.B:g0 + (rank + 1) * x.B].copy()).pin_memory())
+        h2d = float(x.B * 4)
+        api = "VAETrainer.train_on_batch(pinned host user-id batch into the resident CSR) -> loss floats"
+    capg = x.cap_global if world > 1 else None
+    for s in range(3):
+        x.trainer.train_on_batch(host[s], b_global=x.Bg, nnz_cap_global=capg)
+    barrier(dev, world)
+    t = 0.0
+    for s in range(KE):
+        flush_buf.fill_(s & 0xFF)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        x.trainer.train_on_batch(host[s], b_global=x.Bg, nnz_cap_global=capg)     # returns python floats -> synchronises
+        t += time.perf_counter() - t0
+    (t,) = dist_max([t], dev, world)
+    return {"value": KE * x.Bg / t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12, "steps": KE, "api": api,
+            "timing": "wall clock around each call (H2D + captured step + D2H of 3 loss floats), max over ranks"}
+
+
+def measure_eval(x, dev, world, rank, max_users=262144):
+    """Full-ranking top-K + Recall/NDCG/HR (evaluate.py:243-265) at the training workload's shape, users sharded over ranks;
+    metric sums are reduced over ranks before the means are formed."""
+    from hvae_b200.dist import split_even
+    from hvae_b200.evaluate import RecommendationEvaluator
+    x.model.eval()
+    ev = RecommendationEvaluator(x.model, x.csr, {}, {}, dev, batch_users=4096)
+    n_eval = min(x.U, max_users)
+    lo, hi = split_even(n_eval, world, rank)
+    users = np.arange(lo, hi, dtype=np.int64)
+    rel_ptr = np.arange(len(users) + 1, dtype=np.int64)
+    rel_idx = x.data.test_items[users].astype(np.int32)
+    kv = [5, 10, 20]
+    w = min(len(users), 4096)
+    ev.evaluate_users(users[:w], rel_ptr[:w + 1], rel_idx[:w], kv)
+    barrier(dev, world)
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        _, idx = ev.topk_users(users, min(max(kv), x.N))
+        res, cnt = ev.metrics_from_topk(idx, rel_ptr, rel_idx, kv)    # host ids in, metric sums out (sync)
+    barrier(dev, world)
+    (t,) = dist_max([(time.perf_counter() - t0) / reps], dev, world)
+    sums = torch.tensor([res[k][m] * cnt for k in kv for m in ("recall", "ndcg", "hit_ratio")] + [float(cnt)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(sums)
+    sums = sums.cpu().numpy()
+    x.model.train()
+    return {"metric": "eval_topk_users_per_sec", "value": n_eval / t, "unit": UNIT, "k_values": kv, "users": n_eval, "items": x.N,
+            "sharding": "users" if world > 1 else "none", "ndcg@10": float(sums[4] / max(sums[-1], 1)), "recall@20": float(sums[6] / max(sums[-1], 1)),
+            "users_evaluated": int(sums[-1]), "timing": "wall clock incl. H2D of user ids and D2H of metric sums, max over ranks"}
+
+
+def dp_parity(x, args, dev, world, rank):
+    """One optimisation step with INJECTED noise on two fresh copies of the model: data parallel over the ranks vs the same
+    global batch on one GPU (every rank recomputes the latter).  -> relative differences of the loss and of the weights."""
+    import torch.distributed as dist
+    from hvae_b200.engine import Batch
+    from hvae_b200.model import HybridVAE
+    from hvae_b200.train import VAETrainer
+    c = x.c
+    sd = x.model.state_dict()
+    Bg, B = x.Bg, x.B
+    rows_g = x.order_dev[:Bg].contiguous()
+    g = torch.Generator(device=dev).manual_seed(1234)
+    keep = 1.0 - c["dropout"]
+    noise_g = dict(masks=[(torch.rand(Bg, h, device=dev, generator=g) < keep).to(torch.uint8) for h in c["hidden_dims"]],
+                   eps=torch.randn(Bg, c["latent_dim"], device=dev, generator=g),
+                   pmask=(torch.rand(Bg, x.d, device=dev, generator=g) < keep).to(torch.uint8))
+    out = {}
+    models = []
+    for mode in ("single", "dp"):
+        torch.manual_seed(0)
+        m = HybridVAE(x.N, np.zeros((x.N, x.d), dtype=np.float32), c["latent_dim"], c["hidden_dims"], c["dropout"], c["beta"], precision=args.precision)
+        m.load_state_dict(sd)
+        tr = VAETrainer(m, dev, lr=1e-3, use_cuda_graph=False)
+        m.train()
+        if mode == "single":
+            cap = int(x.lens[x.order[:Bg]].sum())
+            tr.train_step(Batch(x.csr, rows_g, Bg, max(1, cap)), noise_g)
+            loss = np.array(tr.last_losses())
+        else:
+            tr.enable_data_parallel()
+            lo, hi = rank * B, (rank + 1) * B
+            nl = dict(masks=[mk[lo:hi].contiguous() for mk in noise_g["masks"]], eps=noise_g["eps"][lo:hi].contiguous(),
+                      pmask=noise_g["pmask"][lo:hi].contiguous())
+            b = Batch(x.csr, rows_g[lo:hi].contiguous(), B, max(1, int(x.lens[x.order[lo:hi]].sum())), b_global=Bg,
+                      nnz_cap_global=int(x.lens[x.order[:Bg]].sum()))
+            tr.train_step(b, nl, b_global=Bg)
+            part = m.engine.loss_out.clone()
+            dist.all_reduce(part)
+            loss = part.cpu().numpy()
+            out["exchange"] = m.engine.dist.exchange
+        out[mode] = loss
+        models.append(m)
+    a, b = models[0].arena.data, models[1].arena.data
+    pdiff = float((a - b).abs().max() / a.abs().max())
+    ldiff = float(np.max(np.abs(out["single"] - out["dp"]) / np.abs(out["single"])))
+    pdiff, ldiff = dist_max([pdiff, ldiff], dev, world)
+    del models
+    gc.collect()
+    torch.cuda.empty_cache()
+    return {"loss_rel_diff": ldiff, "param_max_rel_diff": pdiff, "global_batch": Bg, "first_step_loss_single_gpu": float(out["single"][0]),
+            "first_step_loss_data_parallel": float(out["dp"][0]), "exchange": out.get("exchange"),
+            "what": "one step with injected noise: data-parallel over the ranks vs the same global batch on one GPU (max over ranks)"}
+
+
+# ---- extras ----------------------------------------------------------------------------------------------------------
+def extra_c2_train(args, dev, flush_buf, lib):
+    """BASELINE.json configs[1] (All_Beauty shape, 512 users per step) on this rank's GPU alone."""
+    a2 = argparse.Namespace(**vars(args))
+    x = build_train("c2", a2, dev, 1, 0)
+    r = measure_train(x, 20, 200, dev, 1, 0, flush_buf, lib)
+    out = {"workload": workload_config("c2", x.c, 1)["workload"], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+           "value_hot_l2": r["value_hot"], "gpu_launches_per_step": r["launches"] / 200, "n_gpus": 1, "steps": 200, "warmup": 20}
+    del x
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_c4(args, dev, world, rank, pk, flush_buf):
+    """BASELINE.json configs[3] shape: users scored against 1M items (d = 768), top-20 + Recall/NDCG/HR.  N > 1: E sharded by
+    item over the ranks (hvae_b200.dist.ShardedEvaluator).  Weights / E are drawn on the device (the CPU initialisation of a
+    1M x 600 layer is not the thing measured).  Also times the HBM-bound kernels at this shape."""
+    import torch.distributed as dist
+    from hvae_b200 import dist as hd
+    from hvae_b200._cabi import p
+    from hvae_b200.engine import Batch, DeviceCSR, Engine, Layout
+    from hvae_b200.evaluate import _metric_tables
+    from hvae_b200.synth import make_interactions
+    N, d, K, U = 1_000_000, 768, 20, 262_144
+    lay = Layout(N, d, 200, [600])
+    g = torch.Generator(device=dev).manual_seed(0)           # same weights on every rank
+    arena = torch.randn(lay.n_params, device=dev, generator=g) * 0.02
+    lay.view(arena, "encoder.1.weight").fill_(1.0)
+    E = torch.nn.functional.normalize(torch.randn(N, d, device=dev, generator=g), dim=1)
+    eng = Engine(lay, arena, E, 0.5, "bf16")
+    data = make_interactions(U, N, 0)
+    csr = DeviceCSR.from_arrays(data.indptr, data.indices, None, N, dev)
+    users = torch.arange(U, dtype=torch.int32, device=dev)
+    rel_ptr = torch.arange(U + 1, dtype=torch.int64, device=dev)
+    rel_idx = torch.from_numpy(data.test_items.astype(np.int32)).to(dev)
+    kvals = [5, 10, 20]
+    disc, idcg = _metric_tables(K)
+    t = lambda v, dt: torch.as_tensor(np.asarray(v), dtype=dt, device=dev)
+    kv, dd, ii = t(kvals, torch.int32), t(disc, torch.float64), t(idcg, torch.float64)
+    out = torch.zeros(len(kvals) * 3 + 1, dtype=torch.float64, device=dev)
+    wsd = torch.empty(148 * (len(kvals) * 3 + 1), dtype=torch.float64, device=dev)
+    topk_all = torch.empty(U, K, dtype=torch.int32, device=dev)
+    mask = torch.empty(U, 4, dtype=torch.int32, device=dev)
+    sev = hd.ShardedEvaluator(eng, csr, K, tile=8192)
+
+    def run():
+        sev.topk(users, topk_all)
+        eng.lib.hit_mask(p(topk_all), U, K, p(rel_ptr), p(rel_idx), p(mask), eng.stream)
+        eng.lib.metrics_reduce(p(mask), p(rel_ptr), U, p(kv), len(kvals), p(dd), p(ii), p(wsd), p(out), eng.stream)
+
+    run()
+    barrier(dev, world)
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    barrier(dev, world)
+    (ms,) = dist_max([e0.elapsed_time(e1) / reps], dev, world)
+    with torch.no_grad():      # the un-sharded path on the first users: same arithmetic per item -> identical ids
+        rows = users[:2048]
+        _, i1 = eng.topk(Batch(csr, rows, rows.shape[0], 1), K)
+    same = bool(torch.equal(i1, topk_all[:rows.shape[0]]))
+    o = out.cpu().numpy()
+    flops = 2.0 * U * N * d
+    res = {"eval_c4": {"metric": "eval_topk_users_per_sec", "value": U / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "users": U, "items": N,
+                       "d": d, "K": K, "ms": ms, "sharding": "items" if world > 1 else "none", "items_per_rank": sev.shard.hi - sev.shard.lo,
+                       "aggregate_tflops": flops / (ms * 1e-3) / 1e12,
+                       "frac_of_sustained_tc_peak_per_gpu": flops / (ms * 1e-3) / 1e12 / world / pk["tc_sustained"],
+                       "ids_equal_unsharded": same, "ndcg@10": float(o[4] / max(o[-1], 1)),
+                       "timing": "CUDA events, max over ranks: encoder + all-gather of user vectors + fused GEMM/top-K + all-gather of "
+                                 "candidates + merge + metrics; one CUDA graph per 8,192-user tile"}}
+    if rank == 0:      # kernel rooflines at the 1M-item shape (this GPU alone)
+        res["kernels_1m_items"] = kernels_1m(eng, csr, users, dev, pk, flush_buf, data)
+    del sev, eng, arena, E
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def kernels_1m(eng, csr, users, dev, pk, flush_buf, data):
+    """gather (encoder layer 1 of an evaluation tile), fp32 top-K scan, fused tcgen05 LSE and top-K kernels: 1M items."""
+    from hvae_b200._cabi import p
+    from hvae_b200.engine import Batch
+    lib, st, lay = eng.lib, eng.stream, eng.lay
+    N, d, h = lay.N, lay.d, lay.hidden[0]
+    ld1 = (h + 3) // 4 * 4
+    out = {}
+
+    def timeit(fn, reps=5):
+        fn(); fn()
+        torch.cuda.synchronize(dev)
+        return float(np.median(timed_events(lambda i: fn(), reps, flush_buf, dev)))
+
+    # 1. gather-sum + LayerNorm + GELU of 65,536 users (W1^T is [1M, 600] fp32)
+    Bq = 65536
+    rows = users[:Bq].contiguous()
+    pre, act = torch.empty(Bq, ld1, device=dev), torch.empty(Bq, ld1, device=dev)
+    mean, rstd = torch.empty(Bq, device=dev), torch.empty(Bq, device=dev)
+    ms = timeit(lambda: lib.gather_ln_fwd(p(csr.indptr), p(csr.indices), None, p(rows), Bq, eng.P("encoder.0.weight"), ld1, h,
+                                          eng.P("encoder.0.bias"), eng.P("encoder.1.weight"), eng.P("encoder.1.bias"), None, 1.0,
+                                          p(pre), p(mean), p(rstd), p(act), st))
+    nnz = float(np.diff(data.indptr)[:Bq].sum())
+    gbytes = nnz * (ld1 * 4 + 4) + Bq * (2 * ld1 * 4 + 16)
+    out["gather_ln_fwd"] = {"ms": ms, "bound": "hbm", "users": Bq, "achieved": gbytes / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                            "frac": gbytes / (ms * 1e-3) / 1e9 / pk["hbm"], "algorithmic_bytes": gbytes}
+    del pre, act
+    # 2. fp32 seen-mask + top-20 scan of 256 materialised score rows
+    R, K = 256, 20
+    S = torch.randn(R, N, device=dev)
+    nc = int(lib.mask_topk_chunks(R, N))
+    cv, ci = torch.empty(R, nc * K, device=dev), torch.empty(R, nc * K, dtype=torch.int32, device=dev)
+    ov, oi = torch.empty(R, K, device=dev), torch.empty(R, K, dtype=torch.int32, device=dev)
+    r256 = users[:R].contiguous()
+    ms = timeit(lambda: lib.mask_topk(p(S), N, R, N, 0, p(csr.indptr), p(csr.indices), p(r256), 1, K, p(cv), p(ci), p(ov), p(oi), st))
+    out["mask_topk"] = {"ms": ms, "bound": "hbm", "rows": R, "achieved": R * N * 4.0 / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": R * N * 4.0 / (ms * 1e-3) / 1e9 / pk["hbm"], "algorithmic_bytes": R * N * 4.0}
+    del S
+    # 3. tcgen05 scoring kernels over the 1M items, 4,096 users
+    B = 4096
+    ld = (d + 7) // 8 * 8
+    g = torch.Generator(device=dev).manual_seed(0)
+    U = (torch.randn(B, ld, generator=g, device=dev) * 0.3).to(torch.bfloat16)
+    Eb = eng.E_bf16
+    ns = int(lib.tc_n_splits(B, N))
+    ws, lse = torch.empty(2 * B * ns, device=dev), torch.empty(B, device=dev)
+    ms = timeit(lambda: lib.tc_score_lse(p(U), ld, B, p(Eb), ld, N, d, p(lse), p(ws), st), 3)
+    fl = 2.0 * B * N * d
+    out["tc_score_lse"] = {"ms": ms, "bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
+                           "frac": fl / (ms * 1e-3) / 1e12 / pk["tc_sustained"], "algorithmic_flops": fl}
+    nst = int(lib.tc_topk_splits(B, N))
+    cv, ci = torch.empty(B, nst * K, device=dev), torch.empty(B, nst * K, dtype=torch.int32, device=dev)
+    r4k = users[:B].contiguous()
+    ms = timeit(lambda: lib.tc_score_topk(p(U), ld, B, p(Eb), ld, N, d, 0, p(csr.indptr), p(csr.indices), p(r4k), K, p(cv), p(ci), st), 3)
+    out["tc_score_topk"] = {"ms": ms, "bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
+                            "frac": fl / (ms * 1e-3) / 1e12 / pk["tc_sustained"], "algorithmic_flops": fl, "K": K}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -194,234 +637,71 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from hvae_b200 import _cabi
-    from hvae_b200.engine import Batch, DeviceCSR
-    from hvae_b200.evaluate import RecommendationEvaluator
-    from hvae_b200.model import HybridVAE
-    from hvae_b200.train import VAETrainer
-
     pk = peaks()
-    c, data, E = make_workload(args.workload, args.batch)
-    B, U, N, d, L, h = c["batch"], c["n_users"], c["n_items"], c["emb_dim"], c["latent_dim"], c["hidden_dims"]
-    torch.manual_seed(0)
-    model = HybridVAE(N, E, L, h, c["dropout"], c["beta"], precision=args.precision)
-    trainer = VAETrainer(model, dev, lr=1e-3, use_cuda_graph=not args.no_graph)
-    dp = trainer.enable_data_parallel() if world > 1 else None
-    eng = model.engine
     lib = _cabi.lib()
-    csr = DeviceCSR.from_arrays(data.indptr, data.indices, None, N, dev)
-
-    # global batches: a fixed permutation of the users, walked cyclically; rank r takes slice r of each global batch
-    Bg = B * world
-    order = np.random.default_rng(0).permutation(U).astype(np.int32)
-    order = np.concatenate([order, order[:Bg]])
-    order_dev = torch.from_numpy(order).to(dev)
-    lens = np.diff(data.indptr)
-    n_batches = U // Bg if U >= Bg else 1
-
-    cap_local = max(int(lens[order[i * Bg + rank * B:i * Bg + (rank + 1) * B]].sum()) for i in range(n_batches))
-    cap_global = max(int(lens[order[i * Bg:(i + 1) * Bg]].sum()) for i in range(n_batches))
-
-    def batch_at(s):
-        g0 = (s % n_batches) * Bg
-        return Batch(csr, order_dev[g0 + rank * B:g0 + (rank + 1) * B], B, max(1, cap_local), b_global=Bg, nnz_cap_global=cap_global)
-
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    model.train()
-
-    def step(s):
-        trainer.train_step(batch_at(s), b_global=Bg)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     W, K = max(args.warmup, 3), args.steps
+
+    x = build_train(args.workload, args, dev, world, rank, args.batch)
+    parity = dp_parity(x, args, dev, world, rank) if world > 1 else None
+
     clocks = ClockSampler(local) if rank == 0 else None
-    for s in range(W):
-        step(s)
-    barrier()
-    # ---- timed region 1 (the `value`): K steps, inputs resident in HBM, per-step CUDA events, L2 flushed between steps
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    l0 = lib.launches
-    t_wall0 = time.perf_counter()
-    for s in range(K):
-        flush_buf.fill_(s & 0xFF)
-        evs[s][0].record()
-        step(W + s)
-        evs[s][1].record()
-    barrier()
-    t_wall1 = time.perf_counter()
-    launches = lib.launches - l0
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
-    # ---- back-to-back (hot L2) variant, one event pair around all K steps
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for s in range(K):
-        step(W + K + s)
-    e1.record()
-    barrier()
-    ms_hot = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total, ms_hot], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_hot = float(t[0]), float(t[1])
-    value = K * Bg / (ms_total * 1e-3)
-    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+    r = measure_train(x, W, K, dev, world, rank, flush_buf, lib)
+    clk = clocks.stop(*r["wall"]) if clocks else None
+    kernels, span_avg, roofline = kernel_spans(x, W, K, flush_buf, pk, world, r["ms_per_step"], args)
+    e2e = measure_e2e(x, K, dev, world, rank, flush_buf)
+    ev_out = None if args.no_eval else measure_eval(x, dev, world, rank)
+    exchange = x.model.engine.dist.exchange if world > 1 else None
+    cfg = workload_config(args.workload, x.c, world)
+    c_cpu, data_cpu, E_cpu = x.c, x.data, x.E
+    x.trainer._graphs.clear()
+    del x
+    gc.collect()
+    torch.cuda.empty_cache()
 
-    # ---- per-kernel-group durations (CUDA events on the launching stream, same steps, un-graphed) -> roofline
-    trainer_graph = trainer.use_cuda_graph
-    trainer.use_cuda_graph = False
-    eng.prof = {}
-    PS = min(K, 50)
-    for s in range(PS):
-        flush_buf.fill_(1)
-        step(W + 2 * K + s)
-    spans = eng.span_ms()
-    eng.prof = None
-    trainer.use_cuda_graph = trainer_graph
-    span_avg = {k: float(np.mean(v)) for k, v in spans.items()}
-    lay = model.layout
-    n_unique_avg = float(np.mean([len(np.unique(np.concatenate([data.indices[data.indptr[u]:data.indptr[u + 1]]
-                                                               for u in order[i * Bg:(i + 1) * Bg]]))) for i in range(min(4, n_batches))]))
-    ld1 = (h[0] + 3) // 4 * 4
-    adam_bytes = 24.0 * lay.n_params + 4.0 * (lay.n_dense + n_unique_avg * ld1)
-    flops_fwd = 2.0 * B * N * d
-    kernels = {}
-    if "adam" in span_avg:
-        kernels["adam"] = {"ms": span_avg["adam"], "bound": "hbm", "achieved": adam_bytes / (span_avg["adam"] * 1e-3) / 1e9, "peak": pk["hbm"],
-                           "unit": "GB/s", "algorithmic_bytes": adam_bytes}
-    if "score_fwd" in span_avg:
-        kernels["score_fwd"] = {"ms": span_avg["score_fwd"], "bound": "tensor", "achieved": flops_fwd / (span_avg["score_fwd"] * 1e-3) / 1e12,
-                                "peak": pk["tc_sustained"], "unit": "TFLOP/s", "algorithmic_flops": flops_fwd}
-    if "score_bwd" in span_avg:
-        kernels["score_bwd"] = {"ms": span_avg["score_bwd"], "bound": "tensor", "achieved": flops_fwd / (span_avg["score_bwd"] * 1e-3) / 1e12,
-                                "peak": pk["tc_sustained"], "unit": "TFLOP/s", "algorithmic_flops": flops_fwd,
-                                "executed_flops": flops_fwd * (1 + -(-((d + 63) // 64 * 64) // 384))}
-    if "score_onepass" in span_avg:     # forward + backward through the scores in one sweep: S = U E^T and O = P E, 2BNd each
-        kernels["score_onepass"] = {"ms": span_avg["score_onepass"], "bound": "tensor",
-                                    "achieved": 2 * flops_fwd / (span_avg["score_onepass"] * 1e-3) / 1e12, "peak": pk["tc_sustained"],
-                                    "unit": "TFLOP/s", "algorithmic_flops": 2 * flops_fwd,
-                                    "executed_flops": flops_fwd * (2 if d <= 768 else 1 + -(-((d + 63) // 64 * 64) // 384)),
-                                    "launches": "one-pass scoring kernel + combine"}
-    if "gather" in span_avg:
-        nnz_avg = float(lens[order[:Bg * min(4, n_batches)]].sum()) / min(4, n_batches) / world
-        gbytes = nnz_avg * (ld1 * 4 + 4) + B * (3 * ld1 * 4 + 16)
-        kernels["gather"] = {"ms": span_avg["gather"], "bound": "hbm", "achieved": gbytes / (span_avg["gather"] * 1e-3) / 1e9, "peak": pk["hbm"],
-                             "unit": "GB/s", "algorithmic_bytes": gbytes}
-    for k in kernels.values():
-        k["frac"] = k["achieved"] / k["peak"]
-    dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
-    traffic = None
-    tf = ROOT / "profiles" / "traffic.json"
-    if tf.exists() and dom:
-        traffic = json.loads(tf.read_text()).get(f"{args.workload}:{args.precision}:{dom}")
-    roofline = None
-    if dom:
-        kd = kernels[dom]
-        roofline = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"],
-                    "frac": kd["frac"], "traffic": traffic, "peak_source": pk["source"] + (" sustained" if kd["bound"] == "tensor" else ""),
-                    "ms_per_launch": kd["ms"],
-                    "share_of_step": kd["ms"] / max(1e-9, sum(v for k, v in span_avg.items() if not k.startswith("score_")))}
-
-    # ---- timed region 2 (`e2e`): public API with HOST (pinned) batches; H2D of the batch and D2H of the loss every step
-    KE = min(K, 200)
-    host_batches = []
-    if world == 1:      # the step's input is the batch's CSR slice (indptr, indices, values) in pinned host memory
-        for s in range(KE):
-            g0 = (s % n_batches) * Bg
-            rows_h = order[g0 + rank * B:g0 + (rank + 1) * B].astype(np.int64)
-            starts, ln = data.indptr[rows_h], lens[rows_h]
-            crow = np.zeros(B + 1, dtype=np.int64)
-            np.cumsum(ln, out=crow[1:])
-            take = np.repeat(starts - crow[:-1], ln) + np.arange(int(ln.sum()), dtype=np.int64)
-            col = data.indices[take].astype(np.int32)
-            x = torch.sparse_csr_tensor(torch.from_numpy(crow).pin_memory(), torch.from_numpy(col).pin_memory(),
-                                        torch.ones(col.shape[0], dtype=torch.float32).pin_memory(), size=(B, N), check_invariants=False)
-            host_batches.append(x)
-        h2d = float(np.mean([x.crow_indices().numel() * 8 + x.col_indices().numel() * 4 + x.values().numel() * 4 for x in host_batches]))
-        e2e_api = "VAETrainer.train_on_batch(pinned host CSR batch) -> loss floats"
-    else:               # data parallel: the interaction CSR is resident on every rank; the step's input is its user ids
-        trainer.set_interactions(csr)
-        for s in range(KE):
-            g0 = (s % n_batches) * Bg
-            host_batches.append(torch.from_numpy(order[g0 + rank * B:g0 + (rank + 1) * B].copy()).pin_memory())
-        h2d = float(B * 4)
-        e2e_api = "VAETrainer.train_on_batch(pinned host user-id batch into the resident CSR) -> loss floats"
-    capg = cap_global if world > 1 else None
-    for s in range(3):
-        trainer.train_on_batch(host_batches[s], b_global=Bg, nnz_cap_global=capg)
-    barrier()
-    t_e2e = 0.0
-    for s in range(KE):
-        flush_buf.fill_(s & 0xFF)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        trainer.train_on_batch(host_batches[s], b_global=Bg, nnz_cap_global=capg)     # returns python floats -> synchronises
-        t_e2e += time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t[0])
-    e2e = {"value": KE * Bg / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12, "steps": KE,
-           "api": e2e_api}
-
-    # ---- evaluation: full-ranking top-K + Recall/NDCG/HR over every user (evaluate.py:243-265), user-sharded over ranks
-    ev_out = None
-    if not args.no_eval:
-        model.eval()
-        ev = RecommendationEvaluator(model, csr, {}, {}, dev, batch_users=4096)
-        from hvae_b200.dist import split_even
-        lo, hi = split_even(U, world, rank)
-        users = np.arange(lo, hi, dtype=np.int64)
-        rel_ptr = np.arange(len(users) + 1, dtype=np.int64)
-        rel_idx = data.test_items[users].astype(np.int32)
-        ev.evaluate_users(users[:min(len(users), 4096)], rel_ptr[:min(len(users), 4096) + 1], rel_idx[:min(len(users), 4096)], [5, 10, 20])
-        barrier()
-        reps = 3
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            res, _ = ev.evaluate_users(users, rel_ptr, rel_idx, [5, 10, 20])    # host ids in, metric sums out (sync)
-        barrier()
-        t_ev = (time.perf_counter() - t0) / reps
-        if world > 1:
-            t = torch.tensor([t_ev], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_ev = float(t[0])
-        ev_out = {"metric": "eval_topk_users_per_sec", "value": U / t_ev, "unit": UNIT, "k_values": [5, 10, 20], "users": U,
-                  "ndcg@10": res[10]["ndcg"], "timing": "wall clock incl. H2D of user ids and D2H of metric sums"}
-        model.train()
+    extra = {"exchange": exchange, "dp_parity": parity, "precision": args.precision}
+    if not args.no_extras:
+        extra["c2_train"] = extra_c2_train(args, dev, flush_buf, lib)
+        extra.update(extra_c4(args, dev, world, rank, pk, flush_buf))
 
     if rank != 0:
-        _finish(world, dist, dev)
-        return
+        return _finish(world, dist, dev)
 
     cpu = None
-    if not args.no_cpu_baseline:
-        ups, n_steps, secs, cores = cpu_reference_run(c, data, E, 10 ** 6, 2, seconds=args.cpu_seconds)
-        cpu = {"value": ups, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_steps} steps of batch {B} ({n_steps * B} users, {secs:.1f} s) of the same workload through "
-                         "oracle/hvae_oracle.py (reference train loop incl. per-row densification)"}
+    if not args.no_cpu_baseline and world == 1:
+        ref = CpuReference(c_cpu, data_cpu, E_cpu)
+        Bs = ref.pick_sample(args.cpu_seconds / 3.0, c_cpu["batch"])
+        ref.step(Bs)
+        n, secs = 0, 0.0
+        while n < 2 or (secs < args.cpu_seconds and n < 50):
+            secs += ref.step(Bs)
+            n += 1
+        cpu = {"value": n * Bs / secs, "unit": UNIT, "cores": ref.threads, "kind": "port",
+               "sample": f"{n} steps of {Bs} users each ({secs:.1f} s; a bounded sample of the {c_cpu['batch']}-user batch of the same workload) "
+                         "through oracle/hvae_oracle.py (the reference's train loop incl. per-row densification)"}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(args.workload, c, world, args.precision),
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
-            "value_hot_l2": K * Bg / (ms_hot * 1e-3), "ms_per_step_hot_l2": ms_hot / K,
-            "kernels": kernels, "spans_ms": span_avg, "eval": ev_out, "cuda_graph": bool(trainer.use_cuda_graph)}
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": cfg,
+            "e2e": e2e, "gpu_launches": r["launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "value_hot_l2": r["value_hot"], "ms_per_step_hot_l2": r["ms_hot"], "kernels": kernels, "spans_ms": span_avg, "eval": ev_out,
+            "cuda_graph": not args.no_graph, "extra": extra}
     print(json.dumps(line), flush=True)
     _finish(world, dist, dev)
 
 
 def _finish(world, dist, dev):
-    """Multi-rank exit: the captured step graphs hold NCCL work, so synchronise and leave without tearing the communicator down
-    (process exit releases it; destroy_process_group() can wait forever on graph-captured collectives)."""
-    if world > 1:
-        torch.cuda.synchronize(dev)
-        sys.stdout.flush()
-        sys.stderr.flush()
+    """Multi-rank exit.  The captured graphs that hold NCCL work were dropped above; tear the communicator down, but never wait
+    for it longer than a few seconds (a rank stuck in destroy_process_group() would stall the whole job)."""
+    if world == 1:
+        return
+    torch.cuda.synchronize(dev)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    th.start()
+    th.join(timeout=15.0)
+    if th.is_alive():
         os._exit(0)
 
 

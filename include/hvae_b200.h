@@ -149,6 +149,10 @@ int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, co
                    float* out_val, int32_t* out_idx, void* stream);
 int hvae_topk_merge(const float* cval, const int32_t* cidx, int n_rows, int GK, int K, float* out_val, int32_t* out_idx,
                     void* stream);
+/* The same merge over the blocks of an all-gather, read in place: rank g's K candidates of row r are at
+ * cval/cidx[g * group_stride + r * K] (item-sharded evaluation: local top-K -> all-gather -> merge). */
+int hvae_topk_merge_groups(const float* cval, const int32_t* cidx, int n_rows, int n_groups, int64_t group_stride, int K,
+                           float* out_val, int32_t* out_idx, void* stream);
 /* Negative-sampling protocol (evaluate.py:149-185): scores of C candidates per row (candidate 0 = test item) and the
  * 0-based rank of candidate 0 under a stable descending sort.  cand: int32 [B, C]; scores may be NULL. */
 int hvae_candidate_rank(const void* U, int ldu, const void* E, int lde, int d, int is_bf16, const int32_t* cand, int C, int B,

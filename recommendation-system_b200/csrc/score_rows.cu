@@ -418,9 +418,12 @@ __global__ void __launch_bounds__(kTopkWarps * 32) mask_topk_kernel(float* __res
     top.store(out_val + ((size_t)r * n_chunks + ch) * K, out_idx + ((size_t)r * n_chunks + ch) * K);
 }
 
-// Merge G sorted candidate lists per row (item-sharded evaluation): cand [n_rows, G*K] -> top K.
+// Merge G candidate lists per row (item-sharded evaluation) -> top K.  Candidate j of row r sits at
+// g * group_stride + r * group_len + (j - g * group_len), g = j / group_len: one [n_rows, GK] array (n_groups = 1, group_len = GK)
+// or the blocks of an all-gather ([rank][n_rows][K]: group_len = K, group_stride = the per-rank block), read in place.
 __global__ void __launch_bounds__(kTopkWarps * 32) topk_merge_kernel(const float* __restrict__ cval, const int32_t* __restrict__ cidx,
-                                                                     int n_rows, int GK, int K, float* __restrict__ out_val,
+                                                                     int n_rows, int n_groups, int group_len, int64_t group_stride,
+                                                                     int K, float* __restrict__ out_val,
                                                                      int32_t* __restrict__ out_idx) {
     pdl_prologue();
     __shared__ float sv_all[kTopkWarps][kMaxK];
@@ -430,15 +433,18 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_merge_kernel(const float
     if (r >= n_rows) return;
     WarpTopK top;
     top.init(K, lane, sv_all[warp], si_all[warp]);
-    const float* cv = cval + (size_t)r * GK;
-    const int32_t* ci = cidx + (size_t)r * GK;
+    const int GK = n_groups * group_len;
+    const float* cv = cval + (size_t)r * group_len;
+    const int32_t* ci = cidx + (size_t)r * group_len;
     for (int base = 0; base < GK; base += 128) {       // four candidates per lane in flight
         float v[4]; int id[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int j = base + q * 32 + lane;
-            v[q] = j < GK ? cv[j] : -INFINITY;
-            id[q] = j < GK ? ci[j] : -1;
+            const int g = j / group_len;
+            const int64_t off = (int64_t)g * group_stride + (j - g * group_len);
+            v[q] = j < GK ? cv[off] : -INFINITY;
+            id[q] = j < GK ? ci[off] : -1;
         }
         const float tv = top.thr_v;
         if (!__any_sync(0xffffffffu, v[0] >= tv || v[1] >= tv || v[2] >= tv || v[3] >= tv)) continue;
@@ -619,7 +625,7 @@ int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, co
     HVAE_LAUNCH_CHECK("mask_topk");
     if (nc > 1) {
         launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, (const float*)cv,
-                   (const int32_t*)ci, n_rows, nc * K, K, out_val, out_idx);
+                   (const int32_t*)ci, n_rows, 1, nc * K, (int64_t)0, K, out_val, out_idx);
         HVAE_LAUNCH_CHECK("mask_topk merge");
     }
     return 0;
@@ -628,8 +634,20 @@ int hvae_mask_topk(float* S, int64_t lds, int n_rows, int N, int item_offset, co
 int hvae_topk_merge(const float* cval, const int32_t* cidx, int n_rows, int GK, int K, float* out_val, int32_t* out_idx, void* stream) {
     HVAE_REQUIRE(K >= 1 && K <= kMaxK, "topk_merge: K=%d outside [1,%d]", K, kMaxK);
     if (n_rows == 0) return 0;
-    launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, cval, cidx, n_rows, GK, K, out_val, out_idx);
+    launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, cval, cidx, n_rows, 1, GK, (int64_t)0, K,
+               out_val, out_idx);
     HVAE_LAUNCH_CHECK("topk_merge");
+    return 0;
+}
+
+// The same merge over the blocks of an all-gather read in place: rank g's K candidates of row r at cval/cidx[g * group_stride + r * K].
+int hvae_topk_merge_groups(const float* cval, const int32_t* cidx, int n_rows, int n_groups, int64_t group_stride, int K, float* out_val,
+                           int32_t* out_idx, void* stream) {
+    HVAE_REQUIRE(K >= 1 && K <= kMaxK && n_groups >= 1, "topk_merge_groups: K=%d outside [1,%d] or no groups", K, kMaxK);
+    if (n_rows == 0) return 0;
+    launch_pdl(topk_merge_kernel, ceil_div(n_rows, kTopkWarps), kTopkWarps * 32, 0, (cudaStream_t)stream, cval, cidx, n_rows, n_groups, K,
+               group_stride, K, out_val, out_idx);
+    HVAE_LAUNCH_CHECK("topk_merge_groups");
     return 0;
 }
 

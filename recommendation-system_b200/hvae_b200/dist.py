@@ -89,6 +89,88 @@ def sharded_topk(eng, batch, K: int, shard: ItemShard, exclude_seen: bool = True
     return out_v, out_i
 
 
+class ShardedEvaluator:
+    """Item-sharded full-ranking evaluation on G ranks (BASELINE.json configs[3]; the reference loop is
+    src/ml/evaluate.py:243-265, one user at a time).  Per tile of `tile` users, captured once as ONE CUDA graph and replayed:
+
+      encoder + projection of tile/G users on each rank (user-sharded: the encoder is not replicated)
+        -> all-gather of the bf16 user vectors (NCCL over NVLink; 6 MB per 4,096 users at d = 768)
+        -> fused tcgen05 GEMM + seen mask + top-K over the rank's item shard, (value, id) written straight into one send block
+        -> ONE all-gather of the packed [value | id] blocks
+        -> merge of the G x K candidates per user read in place from the gathered blocks (hvae_topk_merge_groups).
+
+    With world == 1 the two collectives drop out.  bf16 mode only (the fp32 path materialises scores: see sharded_topk)."""
+
+    def __init__(self, eng, csr, K: int, group=None, tile: int = 4096, use_graph: bool = True):
+        from . import tc
+        if eng.precision == "fp32" or K > tc.MAX_K_TC:
+            raise RuntimeError("ShardedEvaluator runs the fused bf16 top-K kernel (K <= %d); use sharded_topk otherwise" % tc.MAX_K_TC)
+        self.eng, self.csr, self.K, self.group = eng, csr, K, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.tile = (tile + self.world - 1) // self.world * self.world
+        self.shard = ItemShard(eng.lay.N, self.world, self.rank)
+        dev, T = eng.dev, self.tile
+        ld8 = (eng.lay.d + 7) // 8 * 8
+        self.rows = torch.zeros(T, dtype=torch.int32, device=dev)                 # static input of the captured tile
+        self.ub_all = torch.zeros(T, ld8, dtype=torch.bfloat16, device=dev)
+        self.ub_send = torch.zeros(T // self.world, ld8, dtype=torch.bfloat16, device=dev)
+        self.send = torch.zeros(2, T, K, dtype=torch.int32, device=dev)           # [value bits | id]
+        self.recv = torch.zeros(self.world, 2, T, K, dtype=torch.int32, device=dev)
+        self.out_val = torch.zeros(T, K, dtype=torch.float32, device=dev)
+        self.out_idx = torch.zeros(T, K, dtype=torch.int32, device=dev)
+        self.use_graph, self._graph = use_graph, None
+
+    def _tile(self):
+        from . import tc
+        from ._cabi import p
+        from .engine import Batch
+        eng, T, K, W = self.eng, self.tile, self.K, self.world
+        bl = T // W
+        mine = self.rows[self.rank * bl:(self.rank + 1) * bl]
+        u = eng.user_vectors(Batch(self.csr, mine, bl, 1))
+        d, ld8 = eng.lay.d, self.ub_all.shape[1]
+        dst = self.ub_send if W > 1 else self.ub_all
+        eng.lib.cast_bf16(p(u), bl, d, (d + 3) // 4 * 4, p(dst), ld8, eng.stream)
+        if W > 1:
+            dist.all_gather_into_tensor(self.ub_all, self.ub_send, group=self.group)
+        full = Batch(self.csr, self.rows, T, 1)
+        if W == 1:
+            tc.topk_bf16_from_ub(eng, full, self.ub_all, K, True, 0, eng.lay.N, self.out_val, self.out_idx)
+            return
+        tc.topk_bf16_from_ub(eng, full, self.ub_all, K, True, self.shard.lo, self.shard.hi, self.send[0].view(torch.float32), self.send[1])
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        eng.lib.topk_merge_groups(p(self.recv), self.recv.data_ptr() + 4 * T * K, T, W, 2 * T * K, K, p(self.out_val), p(self.out_idx),
+                                  eng.stream)
+
+    def run_tile(self):
+        if not self.use_graph:
+            return self._tile()
+        if self._graph is None:
+            self._tile()                                   # allocates every workspace
+            torch.cuda.synchronize(self.eng.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._tile()
+            self._graph = g
+            return
+        self._graph.replay()
+
+    def topk(self, users: torch.Tensor, out_idx: torch.Tensor = None):
+        """Top-K item ids [n, K] (int32, device) of `users` (device int32 ids; every rank passes the same list)."""
+        n, T = users.shape[0], self.tile
+        out = out_idx if out_idx is not None else torch.empty(n, self.K, dtype=torch.int32, device=self.eng.dev)
+        with torch.no_grad():
+            for s in range(0, n, T):
+                m = min(T, n - s)
+                self.rows[:m].copy_(users[s:s + m])
+                if m < T:
+                    self.rows[m:].fill_(int(users[0]))      # pad slots repeat a valid user; their results are dropped
+                self.run_tile()
+                out[s:s + m].copy_(self.out_idx[:m])
+        return out
+
+
 class DataParallel:
     """Gradient exchange of data-parallel training; installed as `engine.dist`."""
 

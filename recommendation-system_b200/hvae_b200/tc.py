@@ -71,12 +71,18 @@ def topk_bf16(eng, batch, u, K, exclude_seen, item_lo, item_hi, out_val, out_idx
     """Fused score + seen-mask + top-K over items [item_lo, item_hi).  False if K is beyond the fused kernel."""
     if K > MAX_K_TC:
         return False
+    return topk_bf16_from_ub(eng, batch, user_vectors_bf16(eng, u, batch.B), K, exclude_seen, item_lo, item_hi, out_val, out_idx)
+
+
+def topk_bf16_from_ub(eng, batch, ub, K, exclude_seen, item_lo, item_hi, out_val, out_idx) -> bool:
+    """The same with the bf16 user vectors [B, r8(d)] already at hand (item-sharded evaluation all-gathers them)."""
+    if K > MAX_K_TC:
+        return False
     lay, ws, lib, st = eng.lay, eng.ws, eng.lib, eng.stream
     B, d = batch.B, lay.d
     ld8 = r8(d)
     n_it = item_hi - item_lo
     Eb = eng.E_bf16
-    ub = user_vectors_bf16(eng, u, B)
     ns = int(lib.tc_topk_splits(B, n_it))
     cv = ws.get("tc_cand_v", (B, ns * K))
     ci = ws.get("tc_cand_i", (B, ns * K), torch.int32)
