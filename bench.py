@@ -468,12 +468,17 @@ def dp_parity(x, args, dev, world, rank):
         models.append(m)
     a, b = models[0].arena.data, models[1].arena.data
     pdiff = float((a - b).abs().max() / a.abs().max())
+    ga, gb = models[0].engine.m, models[1].engine.m          # first Adam moment after one step = (1 - beta1) * clipped gradient
+    gdiff = float((ga - gb).abs().max() / ga.abs().max())
     ldiff = float(np.max(np.abs(out["single"] - out["dp"]) / np.abs(out["single"])))
-    pdiff, ldiff = dist_max([pdiff, ldiff], dev, world)
+    pdiff, ldiff, gdiff = dist_max([pdiff, ldiff, gdiff], dev, world)
     del models
     gc.collect()
     torch.cuda.empty_cache()
-    return {"loss_rel_diff": ldiff, "param_max_rel_diff": pdiff, "global_batch": Bg, "first_step_loss_single_gpu": float(out["single"][0]),
+    return {"loss_rel_diff": ldiff, "grad_max_rel_diff": gdiff, "param_max_rel_diff": pdiff,
+            "note": "the first Adam step moves every weight by +-lr whatever the size of its gradient, so a last-bit difference of a "
+                    "near-zero gradient entry shows up as 2*lr in param_max_rel_diff; grad_max_rel_diff is the meaningful number",
+            "global_batch": Bg, "first_step_loss_single_gpu": float(out["single"][0]),
             "first_step_loss_data_parallel": float(out["dp"][0]), "exchange": out.get("exchange"),
             "what": "one step with injected noise: data-parallel over the ranks vs the same global batch on one GPU (max over ranks)"}
 

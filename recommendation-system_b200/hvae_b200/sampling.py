@@ -82,12 +82,20 @@ def candidate_ranks(ev, users, cand: np.ndarray):
     return ranks.cpu().numpy()
 
 
-def evaluate_with_negatives(ev, users, tests, n_negatives, k_values, seed=None):
-    rng = np.random.default_rng(seed)
-    csr = ev._csr
-    indptr = csr.indptr.cpu().numpy()
-    indices = csr.indices.cpu().numpy()
-    cand, valid = sample_negatives(indptr, indices, ev.n_items, users, tests, n_negatives, rng)
+def evaluate_with_negatives(ev, users, tests, n_negatives, k_values, seed=None, negatives=None):
+    """`negatives` [n, n_negatives] (optional): use these candidates instead of drawing them -- how a run of the reference,
+    whose draws come from the unseeded np.random (src/ml/evaluate.py:169, tune.py:163), is replayed exactly."""
+    if negatives is not None:
+        negatives = np.asarray(negatives, dtype=np.int32)
+        n_negatives = negatives.shape[1]
+        cand = np.concatenate([np.asarray(tests, dtype=np.int32)[:, None], negatives], axis=1)
+        valid = np.full(cand.shape[0], n_negatives, dtype=np.int32)
+    else:
+        rng = np.random.default_rng(seed)
+        csr = ev._csr
+        indptr = csr.indptr.cpu().numpy()
+        indices = csr.indices.cpu().numpy()
+        cand, valid = sample_negatives(indptr, indices, ev.n_items, users, tests, n_negatives, rng)
     ranks = candidate_ranks(ev, users, cand).astype(np.int64)
     short = valid < n_negatives
     if short.any():       # padded slots repeat the test item (score == test score -> counted as ahead): remove them

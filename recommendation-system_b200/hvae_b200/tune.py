@@ -53,17 +53,18 @@ def train_single_config(model, train_loader, val_loader, device, learning_rate: 
     return best_val_loss, best_epoch
 
 
-def evaluate_pairs_with_negatives(model, matrix, users, items, device, n_negatives=99, k_values=None, seed=None):
+def evaluate_pairs_with_negatives(model, matrix, users, items, device, n_negatives=99, k_values=None, seed=None, negatives=None):
     """99-negative metrics for (user index, held-out item index) pairs; scores from `matrix` rows."""
     k_values = k_values or [10]
     ev = RecommendationEvaluator(model, matrix, {}, {}, device)
-    res = sampling.evaluate_with_negatives(ev, np.asarray(users), np.asarray(items), n_negatives, list(k_values), seed)
+    res = sampling.evaluate_with_negatives(ev, np.asarray(users), np.asarray(items), n_negatives, list(k_values), seed, negatives)
     return {f"{metric}@{k}": res[k][metric] for k in k_values for metric in ("recall", "ndcg", "hit_ratio")}
 
 
 def evaluate_config_on_val(model, train_matrix, val_df, user_to_idx: dict, item_to_idx: dict, device, n_negatives: int = 99,
-                           k_values: list[int] | None = None, seed=None) -> dict[str, float]:
-    """src/ml/tune.py:121-184: one row per (user, held-out validation item), input = the user's train row."""
+                           k_values: list[int] | None = None, seed=None, negatives=None) -> dict[str, float]:
+    """src/ml/tune.py:121-184: one row per (user, held-out validation item), input = the user's train row.
+    `negatives` [kept rows, n_negatives]: replay given draws (the reference's come from the unseeded np.random)."""
     users, items = [], []
     for user_id, item_id in zip(val_df["user_id"].values, val_df["asin"].values):
         if user_id in user_to_idx and item_id in item_to_idx:
@@ -72,7 +73,7 @@ def evaluate_config_on_val(model, train_matrix, val_df, user_to_idx: dict, item_
     k_values = k_values or [10]
     if not users:
         return {f"{metric}@{k}": 0.0 for k in k_values for metric in ("recall", "ndcg", "hit_ratio")}
-    return evaluate_pairs_with_negatives(model, train_matrix, users, items, device, n_negatives, k_values, seed)
+    return evaluate_pairs_with_negatives(model, train_matrix, users, items, device, n_negatives, k_values, seed, negatives)
 
 
 def _dist():
