@@ -22,7 +22,9 @@ namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int MAXK_TC = 32;  // top-K list per row kept in shared memory
+constexpr int MAXK_REG = 32;   // top-K list per row in REGISTERS (sorted 64-bit keys): K <= 32
+constexpr int MAXK_TC = 128;   // larger K (the API's top_k <= 100): list per row in shared memory, 2-stage operand ring
+constexpr int STAGES_SMEM_LIST = 2;
 constexpr float kLog2e = 1.4426950408889634f;
 
 enum Mode { MODE_LSE = 0, MODE_TOPK = 1 };
@@ -58,15 +60,30 @@ struct __align__(8) PipeBarriers {
     uint32_t tmem_base;
 };
 
+// (score, item id) as ONE 64-bit key whose unsigned order is the evaluator's total order (score desc, index desc):
+// the score's bits made monotonic in the high word, the id in the low word; 0 = empty slot (below every real key).
+__device__ __forceinline__ uint64_t topk_key(float v, int idx) {
+    uint32_t u = __float_as_uint(v + 0.0f);                     // -0.0 -> +0.0: equal scores must tie
+    u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+    return (uint64_t(u) << 32) | uint32_t(idx);
+}
+__device__ __forceinline__ float topk_key_value(uint64_t k) {
+    uint32_t u = uint32_t(k >> 32);
+    u ^= (u >> 31) ? 0x80000000u : 0xFFFFFFFFu;
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ bool better(float v, int i, float tv, int ti) { return v > tv || (v == tv && i > ti); }
 
-template <int MODE>
+// STG = operand ring depth; KREG > 0: top-K list of KREG >= K sorted keys per row in registers, KREG == 0: list in shared memory.
+template <int MODE, int STG, int KREG>
 __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_constant__ CUtensorMap tmU,
                                                              const __grid_constant__ CUtensorMap tmE, StatsParams P) {
+    constexpr int STAGES = STG;      // (shadows the file-level default)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + STAGES * STAGE_BYTES);
-    float* list_v = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);           // [128][K]   (TOPK)
+    float* list_v = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);           // [128][K]   (TOPK, shared-memory list)
     int* list_i = reinterpret_cast<int*>(list_v + BM * (MAXK_TC + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,8 +158,14 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
         int* li = list_i + r_local * (MAXK_TC + 1);
         int64_t seen_p = 0, seen_e = 0;
         int next_seen = INT_MAX;
+        // register list (KREG > 0): the best KREG >= K keys seen so far, sorted descending; key[KREG-1] is the admission threshold
+        constexpr int KR = KREG > 0 ? KREG : 1;
+        uint64_t key[KR];
+#pragma unroll
+        for (int e = 0; e < KR; ++e) key[e] = 0;
         if (MODE == MODE_TOPK) {
-            for (int e = 0; e < P.K; ++e) { lv[e] = -INFINITY; li[e] = -1; }
+            if (KREG == 0)
+                for (int e = 0; e < P.K; ++e) { lv[e] = -INFINITY; li[e] = -1; }
             if (row_ok && P.indptr) {
                 const int u = P.rows ? P.rows[row] : row;
                 seen_p = P.indptr[u];
@@ -211,7 +234,11 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
 #pragma unroll
                         for (int t = 1; t < 32; ++t) x = (t == j) ? v[t] : x;
                         const int lc = c * 32 + j, gi = P.item_offset + col0 + lc;
-                        if (cnt == P.K && !better(x, gi, thr_v, thr_i)) continue;
+                        uint64_t xk = 0;
+                        if (KREG > 0) {
+                            xk = topk_key(x, gi);
+                            if (xk <= key[KR - 1]) continue;
+                        } else if (cnt == P.K && !better(x, gi, thr_v, thr_i)) continue;
                         if (nmask) {
                             bool seen = false;
                             if (nmask <= 16) {
@@ -224,17 +251,29 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
                             }
                             if (seen) continue;
                         }
-                        int pos = thr_pos;
-                        if (cnt < P.K) pos = cnt++;
-                        lv[pos] = x;
-                        li[pos] = gi;
-                        if (cnt == P.K) {  // recompute the list's worst element (= threshold)
-                            float wv = lv[0]; int wi = li[0], wp = 0;
-                            for (int e = 1; e < P.K; ++e) {
-                                const float ev = lv[e]; const int ei = li[e];
-                                if (better(wv, wi, ev, ei)) { wv = ev; wi = ei; wp = e; }
+                        if (KREG > 0) {
+                            // sorted insertion without memory traffic or dependent loads: entry e takes its upper neighbour if the
+                            // new key ranks above that neighbour, the new key if it ranks above entry e only
+                            bool above[KR];
+#pragma unroll
+                            for (int e = 0; e < KR; ++e) above[e] = xk > key[e];
+#pragma unroll
+                            for (int e = KR - 1; e >= 1; --e) key[e] = above[e - 1] ? key[e - 1] : (above[e] ? xk : key[e]);
+                            key[0] = above[0] ? xk : key[0];
+                            thr_v = key[KR - 1] ? topk_key_value(key[KR - 1]) : -INFINITY;
+                        } else {
+                            int pos = thr_pos;
+                            if (cnt < P.K) pos = cnt++;
+                            lv[pos] = x;
+                            li[pos] = gi;
+                            if (cnt == P.K) {  // recompute the list's worst element (= threshold)
+                                float wv = lv[0]; int wi = li[0], wp = 0;
+                                for (int e = 1; e < P.K; ++e) {
+                                    const float ev = lv[e]; const int ei = li[e];
+                                    if (better(wv, wi, ev, ei)) { wv = ev; wi = ei; wp = e; }
+                                }
+                                thr_v = wv; thr_i = wi; thr_pos = wp;
                             }
-                            thr_v = wv; thr_i = wi; thr_pos = wp;
                         }
                     }
                 }
@@ -250,7 +289,13 @@ __global__ void __launch_bounds__(192, 1) score_stats_kernel(const __grid_consta
             } else {
                 float* ov = P.cand_val + ((size_t)row * P.n_splits + split) * P.K;
                 int32_t* oi = P.cand_idx + ((size_t)row * P.n_splits + split) * P.K;
-                for (int e = 0; e < P.K; ++e) { ov[e] = lv[e]; oi[e] = li[e]; }
+                if (KREG > 0) {
+#pragma unroll
+                    for (int e = 0; e < KR; ++e)
+                        if (e < P.K) { ov[e] = key[e] ? topk_key_value(key[e]) : -INFINITY; oi[e] = key[e] ? (int32_t)(uint32_t)key[e] : -1; }
+                } else {
+                    for (int e = 0; e < P.K; ++e) { ov[e] = lv[e]; oi[e] = li[e]; }
+                }
             }
         }
     }
@@ -901,7 +946,8 @@ static int pick_topk_splits(int m_tiles, int n_tiles) {
     return (n_tiles + tps - 1) / tps;
 }
 
-constexpr size_t kStatsSmem = STAGES * STAGE_BYTES + 256 + BM * (MAXK_TC + 1) * 8 + 1024;
+constexpr size_t kStatsSmem = STAGES * STAGE_BYTES + 256 + 1024;                                        // LSE, register-list top-K
+constexpr size_t kStatsSmemList = STAGES_SMEM_LIST * STAGE_BYTES + 256 + BM * (MAXK_TC + 1) * 8 + 1024;   // shared-memory-list top-K
 
 }  // namespace tc
 }  // namespace hvae
@@ -936,10 +982,10 @@ static int launch_stats_lse(const void* U, int ldu, int B, const void* E, int ld
     P.part_l = workspace + (size_t)B * P.n_splits;
     static bool attr_set = false;
     if (!attr_set) {
-        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_LSE, STAGES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
         attr_set = true;
     }
-    launch_pdl(score_stats_kernel<MODE_LSE>, dim3(m_tiles, P.n_splits), 192, kStatsSmem, stream, tmU, tmE, P);
+    launch_pdl(score_stats_kernel<MODE_LSE, STAGES, 0>, dim3(m_tiles, P.n_splits), 192, kStatsSmem, stream, tmU, tmE, P);
     HVAE_LAUNCH_CHECK("tc_score_lse");
     *n_splits = P.n_splits;
     return 0;
@@ -1036,7 +1082,7 @@ int hvae_tc_score_lse_grad(const void* U, int ldu, int B, const void* E, int lde
 }
 
 // Top-K over the N items of E (global ids item_offset..item_offset+N).  cand_val / cand_idx: [B, n_splits*K] scratch;
-// the caller reduces them with hvae_topk_merge.  K <= 32.
+// the caller reduces them with hvae_topk_merge.  K <= 128 (K <= 32: register-resident lists; above: shared-memory lists).
 int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, int N, int d, int item_offset, const int64_t* indptr,
                        const int32_t* indices, const int32_t* rows, int K, float* cand_val, int32_t* cand_idx, void* stream) {
     if (B == 0) return 0;
@@ -1053,10 +1099,22 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
     P.indptr = indptr; P.indices = indices; P.rows = rows;
     static bool attr_set = false;
     if (!attr_set) {
-        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES_SMEM_LIST, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kStatsSmemList));
         attr_set = true;
     }
-    launch_pdl(score_stats_kernel<MODE_TOPK>, dim3(m_tiles, P.n_splits), 192, kStatsSmem, (cudaStream_t)stream, tmU, tmE, P);
+    const dim3 grid(m_tiles, P.n_splits);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the list capacity is a compile-time size (register arrays): the smallest bucket that holds K
+    if (K <= 8) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 8>, grid, 192, kStatsSmem, st, tmU, tmE, P);
+    else if (K <= 16) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 16>, grid, 192, kStatsSmem, st, tmU, tmE, P);
+    else if (K <= 24) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 24>, grid, 192, kStatsSmem, st, tmU, tmE, P);
+    else if (K <= MAXK_REG) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 32>, grid, 192, kStatsSmem, st, tmU, tmE, P);
+    else launch_pdl(score_stats_kernel<MODE_TOPK, STAGES_SMEM_LIST, 0>, grid, 192, kStatsSmemList, st, tmU, tmE, P);
     HVAE_LAUNCH_CHECK("tc_score_topk");
     return 0;
 }

@@ -13,7 +13,7 @@ import torch
 from ._cabi import p
 from .engine import r4, r8
 
-MAX_K_TC = 32
+MAX_K_TC = 128       # K <= 32: register-resident lists in the epilogue; K <= 128: shared-memory lists
 
 
 def user_vectors_bf16(eng, u, B):

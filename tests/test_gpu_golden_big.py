@@ -87,10 +87,12 @@ def test_d768_scores_and_topk_match_reference(dev):
         with torch.no_grad():
             x8 = torch.from_numpy(np.asarray(c.csr[:8].toarray(), dtype=np.float32)).to(dev)
             s8, mu8, lv8 = m(x8)
-        # 768-term fp32 dot products in a different summation order: a few 1e-5 absolute on scores of magnitude 1..5
-        np.testing.assert_allclose(s8.cpu().numpy(), c.z["fwd8/scores"], rtol=2e-5, atol=1e-4)
-        np.testing.assert_allclose(mu8.cpu().numpy(), c.z["fwd8/mu"], rtol=1e-5, atol=1e-5)
-        np.testing.assert_allclose(lv8.cpu().numpy(), c.z["fwd8/logvar"], rtol=1e-5, atol=1e-5)
+        # fp32: 768-term dot products in a different summation order, a few 1e-5 absolute on scores of magnitude 1..5;
+        # bf16 mode runs the MLP stack with TF32 operands (10-bit mantissa): 1e-3-level agreement
+        rt, at_s, at = (2e-5, 1e-4, 1e-5) if precision == "fp32" else (5e-3, 2e-2, 5e-3)
+        np.testing.assert_allclose(s8.cpu().numpy(), c.z["fwd8/scores"], rtol=rt, atol=at_s)
+        np.testing.assert_allclose(mu8.cpu().numpy(), c.z["fwd8/mu"], rtol=rt, atol=at)
+        np.testing.assert_allclose(lv8.cpu().numpy(), c.z["fwd8/logvar"], rtol=rt, atol=at)
         ev = RecommendationEvaluator(m, c.csr, {}, {}, dev)
         _, idx = ev.topk_users(np.arange(64), 20)
         got = idx.cpu().numpy()

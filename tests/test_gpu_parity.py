@@ -455,7 +455,7 @@ def test_resume_continues_bit_identically(dev, tmp_path):
 
 
 def test_bf16_large_k_and_recommend(dev):
-    """K beyond the fused epilogue (API top_k <= 100, src/api/schemas.py:8) falls back to the materialised path; recommend()."""
+    """The API's top_k <= 100 (src/api/schemas.py:8) stays on the fused tensor-core kernel (shared-memory lists for K > 32); recommend()."""
     from hvae_b200.evaluate import RecommendationEvaluator
     c = Case("tiny_two_hidden")
     m = _build(c, dev, precision="bf16", state="final")

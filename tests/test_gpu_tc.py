@@ -52,7 +52,8 @@ def test_tc_lse_matches_torch(dev, B, N, d):
     np.testing.assert_allclose(lse.cpu().numpy(), ref.cpu().numpy(), rtol=2e-6, atol=2e-5)
 
 
-@pytest.mark.parametrize("B,N,d,K", [(512, 12101, 384, 20), (77, 1000, 64, 10), (300, 5000, 768, 32), (130, 890, 384, 5), (3, 40, 24, 20)])
+@pytest.mark.parametrize("B,N,d,K", [(512, 12101, 384, 20), (77, 1000, 64, 10), (300, 5000, 768, 32), (130, 890, 384, 5), (3, 40, 24, 20),
+                                     (300, 5000, 768, 100), (77, 1000, 64, 64), (512, 12101, 384, 128), (200, 9000, 200, 33), (64, 70000, 64, 24)])
 def test_tc_topk_matches_torch(dev, B, N, d, K):
     from hvae_b200 import _cabi
     from hvae_b200.synth import make_interactions
