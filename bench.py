@@ -544,10 +544,16 @@ def extra_c4(args, dev, world, rank, pk, flush_buf):
     e1.record()
     barrier(dev, world)
     (ms,) = dist_max([e0.elapsed_time(e1) / reps], dev, world)
-    with torch.no_grad():      # the un-sharded path on the first users: same arithmetic per item -> identical ids
-        rows = users[:2048]
-        _, i1 = eng.topk(Batch(csr, rows, rows.shape[0], 1), K)
-    same = bool(torch.equal(i1, topk_all[:rows.shape[0]]))
+    # sharding + merge against the un-sharded kernel on the SAME user vectors (the last tile's all-gathered ones): the same
+    # arithmetic per item, so the ids must be identical.  (Encoding a different number of users per launch changes the
+    # split-K of the TF32 MLP GEMMs, i.e. the last bits of u: not a property of the sharding.)
+    from hvae_b200 import tc
+    with torch.no_grad():
+        T = sev.tile
+        v1 = torch.empty(T, K, dtype=torch.float32, device=dev)
+        i1 = torch.empty(T, K, dtype=torch.int32, device=dev)
+        tc.topk_bf16_from_ub(eng, Batch(csr, sev.rows, T, 1), sev.ub_all, K, True, 0, N, v1, i1)
+    same = bool(torch.equal(i1, sev.out_idx))
     o = out.cpu().numpy()
     flops = 2.0 * U * N * d
     res = {"eval_c4": {"metric": "eval_topk_users_per_sec", "value": U / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "users": U, "items": N,

@@ -422,8 +422,12 @@ __global__ void w1_expand_kernel(const int32_t* __restrict__ n_unique, const int
     for (int w = w0; w < w1; ++w) work_slot[w] = sl;
     if (w1 - w0 > 1) multi_slot[atomicAdd(n_multi, 1)] = sl;
 }
+// One WARP per work item, a persistent grid striding over the items: most touched items of a Zipf catalogue have one or two
+// entries, so a CTA per item (with a shared-memory reduction over its warps, and a grid sized for the worst case whose CTAs
+// mostly exit at once) spent its time on launch overhead and barriers -- 0.55 ms at the 8-GPU global batch.  The warp adds the
+// item's entries in their (stable, item-sorted) order, up to four dH rows in flight; the sum order is fixed, hence deterministic.
 template <int NCHUNK>
-__global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_work,
+__global__ void __launch_bounds__(256) w1_grad_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_work,
                                                       const int32_t* __restrict__ work_slot, const int32_t* __restrict__ chunk_base,
                                                       const int32_t* __restrict__ part_base,
                                                       const int32_t* __restrict__ sorted_eid, const int32_t* __restrict__ ent_user,
@@ -433,81 +437,64 @@ __global__ void __launch_bounds__(128) w1_grad_kernel(const int32_t* __restrict_
     pdl_prologue();
     // dpre row of batch position u: blocks of `block_rows` rows, `block_stride4` float4 apart (data-parallel training reads
     // the all-gathered per-rank buffers in place); a plain [rows, ld] matrix has block_rows = INT_MAX.
-    extern __shared__ float4 red[];  // [4][ld4]
-    const int w = blockIdx.x;
-    if (w >= *n_work) return;
-    const int slot = work_slot[w];
-    const int cb = chunk_base[slot], nchunks = chunk_base[slot + 1] - cb, chunk = w - cb;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = seg_start[slot] + chunk * kW1Chunk, e = min(seg_start[slot + 1], s + kW1Chunk);
-    float* out_row = nchunks == 1 ? gs + (size_t)slot * ld4 * 4 : partial + (size_t)(part_base[slot] + chunk) * ld4 * 4;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int nw = *n_work;
     const float4* dp = reinterpret_cast<const float4*>(dpre);
-    float4 a[NCHUNK];
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nw; w += warps) {
+        const int slot = work_slot[w];
+        const int cb = chunk_base[slot], nchunks = chunk_base[slot + 1] - cb, chunk = w - cb;
+        const int s = seg_start[slot] + chunk * kW1Chunk, e = min(seg_start[slot + 1], s + kW1Chunk);
+        float* out_row = nchunks == 1 ? gs + (size_t)slot * ld4 * 4 : partial + (size_t)(part_base[slot] + chunk) * ld4 * 4;
+        float4 a[NCHUNK];
 #pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) a[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = s + warp; base < e; base += 4 * 32) {
-        const int mine = base + 4 * lane;
-        int my_user = 0;
-        float my_val = 0.f;
-        if (mine < e) { const int eid = sorted_eid[mine]; my_user = ent_user[eid]; my_val = ent_val[eid]; }
-        const int cnt = min(32, (e - base + 3) / 4);
-        int t = 0;
-        for (; t + 2 <= cnt; t += 2) {
-            const int u0 = __shfl_sync(0xffffffffu, my_user, t), u1 = __shfl_sync(0xffffffffu, my_user, t + 1);
-            const float v0 = __shfl_sync(0xffffffffu, my_val, t), v1 = __shfl_sync(0xffffffffu, my_val, t + 1);
-            const size_t o0 = (size_t)(u0 / block_rows) * block_stride4 + (size_t)(u0 % block_rows) * ld4;
-            const size_t o1 = (size_t)(u1 / block_rows) * block_stride4 + (size_t)(u1 % block_rows) * ld4;
-            float4 g0[NCHUNK], g1[NCHUNK];
+        for (int c = 0; c < NCHUNK; ++c) a[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int base = s; base < e; base += 32) {
+            const int cnt = min(32, e - base);
+            int my_user = 0;
+            float my_val = 0.f;
+            if (lane < cnt) { const int eid = sorted_eid[base + lane]; my_user = ent_user[eid]; my_val = ent_val[eid]; }
+            constexpr int R = NCHUNK <= 6 ? 4 : NCHUNK <= 8 ? 2 : 1;        // dH rows in flight (register budget)
+            for (int t = 0; t < cnt; t += R) {
+                float4 g[R][NCHUNK];
+                float v[R];
 #pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                const int col4 = lane + 32 * c;
-                if (col4 < ld4) { g0[c] = __ldg(dp + o0 + col4); g1[c] = __ldg(dp + o1 + col4); }
-                else { g0[c] = make_float4(0.f, 0.f, 0.f, 0.f); g1[c] = g0[c]; }
-            }
+                for (int r = 0; r < R; ++r) {
+                    const int tt = min(t + r, cnt - 1);                  // clamped; its weight is zeroed below
+                    const int u = __shfl_sync(0xffffffffu, my_user, tt);
+                    v[r] = t + r < cnt ? __shfl_sync(0xffffffffu, my_val, tt) : 0.f;
+                    const size_t o = (size_t)(u / block_rows) * block_stride4 + (size_t)(u % block_rows) * ld4;
 #pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                a[c].x = fmaf(v0, g0[c].x, a[c].x); a[c].y = fmaf(v0, g0[c].y, a[c].y);
-                a[c].z = fmaf(v0, g0[c].z, a[c].z); a[c].w = fmaf(v0, g0[c].w, a[c].w);
-                a[c].x = fmaf(v1, g1[c].x, a[c].x); a[c].y = fmaf(v1, g1[c].y, a[c].y);
-                a[c].z = fmaf(v1, g1[c].z, a[c].z); a[c].w = fmaf(v1, g1[c].w, a[c].w);
-            }
-        }
-        if (t < cnt) {
-            const int u0 = __shfl_sync(0xffffffffu, my_user, t);
-            const float v0 = __shfl_sync(0xffffffffu, my_val, t);
-            const size_t o0 = (size_t)(u0 / block_rows) * block_stride4 + (size_t)(u0 % block_rows) * ld4;
+                    for (int c = 0; c < NCHUNK; ++c) {
+                        const int col4 = lane + 32 * c;
+                        g[r][c] = col4 < ld4 ? __ldg(dp + o + col4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
 #pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                const int col4 = lane + 32 * c;
-                if (col4 < ld4) {
-                    const float4 g = __ldg(dp + o0 + col4);
-                    a[c].x = fmaf(v0, g.x, a[c].x); a[c].y = fmaf(v0, g.y, a[c].y);
-                    a[c].z = fmaf(v0, g.z, a[c].z); a[c].w = fmaf(v0, g.w, a[c].w);
+                for (int r = 0; r < R; ++r) {
+                    if (t + r >= cnt) break;                             // (a zero weight would still turn an inf into a NaN)
+#pragma unroll
+                    for (int c = 0; c < NCHUNK; ++c) {
+                        a[c].x = fmaf(v[r], g[r][c].x, a[c].x); a[c].y = fmaf(v[r], g[r][c].y, a[c].y);
+                        a[c].z = fmaf(v[r], g[r][c].z, a[c].z); a[c].w = fmaf(v[r], g[r][c].w, a[c].w);
+                    }
                 }
             }
         }
-    }
+        float n2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) {
-        const int col4 = lane + 32 * c;
-        if (col4 < ld4) red[warp * ld4 + col4] = a[c];
+        for (int c = 0; c < NCHUNK; ++c) {
+            const int col4 = lane + 32 * c;
+            if (col4 < ld4) {
+                reinterpret_cast<float4*>(out_row)[col4] = a[c];
+                n2 += a[c].x * a[c].x + a[c].y * a[c].y + a[c].z * a[c].z + a[c].w * a[c].w;
+            }
+        }
+        if (nchunks == 1) {            // (the norm of a multi-chunk row is taken after the combine)
+            n2 = warp_sum(n2);
+            if (lane == 0) rownorm2[slot] = n2;
+        }
     }
-    __syncthreads();
-    float n2 = 0.f;
-    for (int col4 = threadIdx.x; col4 < ld4; col4 += 128) {
-        const float4 a0 = red[col4], b = red[ld4 + col4], c = red[2 * ld4 + col4], d = red[3 * ld4 + col4];
-        float4 o;
-        o.x = (a0.x + b.x) + (c.x + d.x); o.y = (a0.y + b.y) + (c.y + d.y);
-        o.z = (a0.z + b.z) + (c.z + d.z); o.w = (a0.w + b.w) + (c.w + d.w);
-        reinterpret_cast<float4*>(out_row)[col4] = o;
-        n2 += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
-    }
-    if (nchunks != 1) return;      // the norm of a multi-chunk row is taken after the combine
-    __shared__ float wsum[4];
-    n2 = warp_sum(n2);
-    if (lane == 0) wsum[warp] = n2;
-    __syncthreads();
-    if (threadIdx.x == 0) rownorm2[slot] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
 }
 
 // Items with several chunks: gs[slot] = partial rows added in chunk order; row norm.  One CTA per multi-chunk slot.
@@ -674,12 +661,11 @@ int hvae_w1_grad(const int32_t* seg_start, const int32_t* n_unique, const int32_
     HVAE_REQUIRE(ld % 4 == 0 && block_stride % 4 == 0, "w1_grad: ld=%d and the block stride must be multiples of 4", ld);
     if (block_rows <= 0) { block_rows = 0x7fffffff; block_stride = 0; }
     if (max_slots == 0) return 0;
-    const size_t smem = (size_t)4 * ld * sizeof(float);
-    HVAE_REQUIRE(smem <= 48 * 1024, "w1_grad: hidden width %d too large", ld);
     const int h = ld;
     const int nch = ceil_div(ld / 4, 32);
     const int max_work = (int)hvae_w1_max_work(max_slots);
-    DISPATCH_NCHUNK(nch, (launch_pdl(w1_grad_kernel<NC>, max_work, 128, smem, (cudaStream_t)stream, 
+    const int grid = max(1, min(kNumSMs * 8, ceil_div(max_work, 8)));      // persistent: 8 warps per CTA stride over the work items
+    DISPATCH_NCHUNK(nch, (launch_pdl(w1_grad_kernel<NC>, grid, 256, 0, (cudaStream_t)stream, 
                              seg_start, n_work, work_slot, chunk_base, part_base, sorted_eid, ent_user, ent_val, dpre, ld / 4, block_rows,
                              block_stride / 4, gs, partial, rownorm2)));
     launch_pdl(w1_combine_kernel, (int)hvae_w1_max_partial_rows(max_slots), 128, 0, (cudaStream_t)stream, n_work + 1, multi_slot, chunk_base,

@@ -212,7 +212,7 @@ int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_p
     HVAE_REQUIRE(n_params % 4 == 0 && n_w1 % 4 == 0 && ld1 % 4 == 0, "adam_step: sizes must be multiples of 4");
     if (n_params == 0) return 0;
     const int64_t n4 = n_params / 4;
-    launch_pdl(adam_kernel, (unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream, 
+    launch_pdl(adam_kernel, (unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream,
         (float4*)params, (float4*)exp_avg, (float4*)exp_avg_sq, n4, n_w1 / 4, ld1 / 4, slot_of_item, (const float4*)gsparse,
         (const float4*)gdense, state, weight_decay, beta1, beta2, eps);
     HVAE_LAUNCH_CHECK("adam_step");
