@@ -8,7 +8,8 @@ Default workload = BASELINE.json configs[2] (C3): 1M users x 200k items, d = 768
 largest single-GPU configuration and the one the 1/2/4/8-GPU scaling is quoted on.  A "step" is one optimisation step
 (forward, multinomial NLL + KL, backward, clip, Adam) over one batch of synthetic users.  Rank 0 prints ONE JSON line;
 besides the contract's keys it carries `extra`: the C2 training step, a C4-shape (1M items) evaluation -- item-sharded over
-the ranks when N > 1 --, kernel rooflines at the 1M-item shape, the gradient-exchange path and a data-parallel parity number.
+the ranks when N > 1 --, kernel rooflines at the 1M-item shape, the C5 grid sweep (16 configurations spread over the ranks), the
+gradient-exchange path and a data-parallel parity number.
 See DESIGN.md §6 for how each field is obtained.
 """
 from __future__ import annotations
@@ -497,6 +498,40 @@ def extra_c2_train(args, dev, flush_buf, lib):
     return out
 
 
+def extra_c5_sweep(args, dev, world, rank, epochs=3):
+    """BASELINE.json configs[4]: 16 (latent_dim, hidden_dims, dropout, beta) configurations at the All_Beauty shape, each trained
+    `epochs` epochs (early stopping, patience 3) + validation NDCG@10 under the 99-negative protocol -- the reference's
+    run_grid_search loop (src/ml/tune.py:187-322).  Configurations are independent: placed round-robin on the ranks, no
+    collective on the data path; the result dicts are gathered at the end (hvae_b200.tune.grid_search_core)."""
+    from scipy.sparse import csr_matrix
+    from hvae_b200.synth import CONFIGS, make_interactions, make_item_embeddings
+    from hvae_b200.tune import grid_search_core
+    c = CONFIGS["c2"]
+    data = make_interactions(c["n_users"], c["n_items"], 0)
+    E = make_item_embeddings(c["n_items"], c["emb_dim"], 0)
+    train = data.scipy_csr()
+    U = c["n_users"]
+    val = csr_matrix((np.ones(U), (np.arange(U), data.test_items)), shape=train.shape)      # 1-hot validation rows (train.py:232,255)
+    space = {"latent_dim": [64, 128], "hidden_dims": [[256], [512]], "dropout": [0.3, 0.5], "beta": [0.1, 0.2], "learning_rate": [1e-3]}
+    torch.manual_seed(0)
+    barrier(dev, world)
+    t0 = time.perf_counter()
+    out = grid_search_core(train, val, list(range(U)), list(range(U)), (np.arange(U), data.test_items.astype(np.int64)), E, space,
+                           epochs_per_config=epochs, patience=3, batch_size=512, use_annealing=True, device=dev, seed=0,
+                           precision=args.precision)
+    torch.cuda.synchronize(dev)
+    (dt,) = dist_max([time.perf_counter() - t0], dev, world)
+    ok = [r for r in out["all_results"] if "error" not in r]
+    steps = epochs * ((U + 511) // 512) * len(ok)
+    gc.collect()
+    torch.cuda.empty_cache()
+    return {"metric": "grid_sweep_seconds", "value": dt, "unit": "s", "n_gpus": world, "configs": len(out["all_results"]),
+            "failed": len(out["all_results"]) - len(ok), "epochs_per_config": epochs, "users": U, "items": c["n_items"],
+            "train_users_per_sec_aggregate": steps * 512 / dt, "best_config": str(out["best_config"]), "best_ndcg@10": out["best_metric"],
+            "placement": "configurations round-robin over the ranks, one process per GPU, no data-path collective",
+            "timing": "wall clock of the whole sweep (16 trainings + 16 validation rankings), max over ranks"}
+
+
 def extra_c4(args, dev, world, rank, pk, flush_buf):
     """BASELINE.json configs[3] shape: users scored against 1M items (d = 768), top-20 + Recall/NDCG/HR.  N > 1: E sharded by
     item over the ranks (hvae_b200.dist.ShardedEvaluator).  Weights / E are drawn on the device (the CPU initialisation of a
@@ -674,6 +709,7 @@ def main():
     if not args.no_extras:
         extra["c2_train"] = extra_c2_train(args, dev, flush_buf, lib)
         extra.update(extra_c4(args, dev, world, rank, pk, flush_buf))
+        extra["c5_sweep"] = extra_c5_sweep(args, dev, world, rank)
 
     if rank != 0:
         return _finish(world, dist, dev)

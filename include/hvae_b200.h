@@ -230,6 +230,23 @@ int hvae_fill_noise(uint8_t* mask, int64_t n_mask, float keep_prob, float* eps, 
 int hvae_nvl_push(const float* src, int64_t n, float* mc_dst, const uint64_t* peer_ptrs, int world, int64_t dst_off,
                   void* stream);
 
+/* ---- Mult-VAE baseline (src/ml/baseline.py:126-231) -- the kernels only that model needs; the rest of it runs on the entry
+ * points above (gather-sum, GEMMs, reparameterise/KL, materialised scoring, item-major gradient reduction, Adam) ------------- */
+/* Input transform on the sparse row: F.normalize(x, p=2, dim=1) then input dropout (baseline.py:151) as per-entry values
+ * out[j] = x_j / max(||x_b||, 1e-12) * keep_j * keep_scale, written at the entries' positions in the global CSR (out has the
+ * CSR's nnz floats).  keep (may be NULL): uint8 flags in batch order, keep_ptr[b] = offset of batch row b's first entry. */
+int hvae_mv_input_values(const int64_t* indptr, const float* values, const int32_t* rows, int B, const uint8_t* keep,
+                         const int32_t* keep_ptr, float keep_scale, float* out, void* stream);
+/* t[B, ldt] = dropout(tanh(q[B, ldq])) over d columns (mask may be NULL), pad columns 0; ones_col >= d: t[:, ones_col] = 1. */
+int hvae_tanh_drop_fwd(const float* q, const uint8_t* mask, float keep_scale, int B, int d, int ldq, float* t, int ldt,
+                       int ones_col, void* stream);
+/* dq[B, ldq] = dt[B, lddt] * mask * keep_scale * (1 - tanh(q)^2) */
+int hvae_tanh_drop_bwd(const float* dt, int lddt, const float* q, const uint8_t* mask, float keep_scale, int B, int d, int ldq,
+                       float* dq, void* stream);
+/* dst[item[s], 0:cols] += alpha * src[s, 0:cols] for s < *n_rows (<= max_rows). */
+int hvae_rows_axpy(const int32_t* item, const int32_t* n_rows, int max_rows, const float* src, int ld_src, float alpha,
+                   float* dst, int ld_dst, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

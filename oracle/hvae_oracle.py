@@ -278,3 +278,58 @@ def cpu_eval_users(model, csr, test_items, users, k_values=(5, 10, 20)):
     t0 = time.perf_counter()
     res, _ = full_ranking_eval(model, csr, test_items, k_values, users)
     return len(list(users)), time.perf_counter() - t0, res
+
+
+# --------------------------------------------------------------------------------------
+# Mult-VAE baseline (src/ml/baseline.py:126-206)
+# --------------------------------------------------------------------------------------
+class OracleMultVAE(nn.Module):
+    """Same module tree (state_dict keys, default nn.Linear initialisation, RNG draw order) as the reference's
+    MultVAE (src/ml/baseline.py:129-149), with a forward that takes its noise as tensors."""
+
+    def __init__(self, n_items, hidden_dim=600, latent_dim=200, dropout=0.5):
+        super().__init__()
+        self.p = dropout
+        self.encoder = nn.Sequential(nn.Linear(n_items, hidden_dim), nn.Tanh(), nn.Dropout(dropout),
+                                     nn.Linear(hidden_dim, hidden_dim), nn.Tanh(), nn.Dropout(dropout))
+        self.mu_layer = nn.Linear(hidden_dim, latent_dim)
+        self.logvar_layer = nn.Linear(hidden_dim, latent_dim)
+        self.decoder = nn.Sequential(nn.Linear(latent_dim, hidden_dim), nn.Tanh(), nn.Linear(hidden_dim, n_items))
+        self.dropout = nn.Dropout(dropout)
+
+    def forward_with(self, x, noise=None):
+        """noise = None (eval) or dict(in_mask [B,N] {0,1}, masks=[[B,h],[B,h]], eps [B,L]) -- baseline.py:150-160."""
+        s = 1.0 / (1.0 - self.p) if noise is not None else 1.0
+        xin = F.normalize(x, p=2, dim=1)
+        if noise is not None:
+            xin = xin * noise["in_mask"] * s
+        h = torch.tanh(self.encoder[0](xin))
+        if noise is not None:
+            h = h * noise["masks"][0] * s
+        h = torch.tanh(self.encoder[3](h))
+        if noise is not None:
+            h = h * noise["masks"][1] * s
+        mu, logvar = self.mu_layer(h), self.logvar_layer(h)
+        z = mu if noise is None else mu + torch.exp(0.5 * logvar) * noise["eps"]
+        return self.decoder(z), mu, logvar
+
+
+def draw_multvae_noise(model: OracleMultVAE, batch: int, n_items: int, hidden_dim: int, latent_dim: int):
+    """The reference's per-step draw order on torch's CPU generator: input dropout over the dense [B, N] row
+    (baseline.py:151), the two encoder dropouts (:139,:142), eps (:155)."""
+    keep = lambda *shape: torch.native_dropout(torch.ones(*shape), model.p, True)[1].float()
+    return dict(in_mask=keep(batch, n_items), masks=[keep(batch, hidden_dim), keep(batch, hidden_dim)],
+                eps=torch.randn(batch, latent_dim))
+
+
+def multvae_train_step(model, opt, x, noise, beta):
+    """baseline.py:196-204: zero_grad, forward, multinomial NLL + beta * KL, backward, Adam step (no gradient clipping)."""
+    model.train()
+    opt.zero_grad()
+    recon, mu, logvar = model.forward_with(x, noise)
+    recon_loss = -torch.mean(torch.sum(F.log_softmax(recon, dim=1) * x, dim=1))
+    kl_loss = -0.5 * torch.mean(torch.sum(1 + logvar - mu.pow(2) - logvar.exp(), dim=1))
+    loss = recon_loss + beta * kl_loss
+    loss.backward()
+    opt.step()
+    return loss.item(), recon_loss.item(), kl_loss.item()

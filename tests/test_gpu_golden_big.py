@@ -80,19 +80,27 @@ def test_d768_scores_and_topk_match_reference(dev):
     for s in range(c.steps):
         orc.train_step(o, opt, torch.from_numpy(np.asarray(c.csr[c.rows(s)].toarray(), dtype=np.float32)), c.noise(s), c.beta)
     c.check_digest("final", _named(o), rtol=2e-5)
+    # Two fp32 executions of two Adam steps agree in the mean but not entry by entry (the first Adam steps move a weight by
+    # +-lr whatever the size of its gradient, so a last-bit difference of a near-zero gradient flips a whole lr): the oracle's
+    # scores sit within 2e-3 of the reference's, and the kernels are held tightly to the oracle ON THE SAME WEIGHTS.
+    o.eval()
+    x8c = torch.from_numpy(np.asarray(c.csr[:8].toarray(), dtype=np.float32))
+    with torch.no_grad():
+        os8, omu8, olv8 = o.forward_with(x8c, None)
+    np.testing.assert_allclose(os8.numpy(), c.z["fwd8/scores"], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(omu8.numpy(), c.z["fwd8/mu"], rtol=2e-3, atol=2e-3)
     for precision in ("fp32", "bf16"):
         m = create_hybrid_vae(**c.model_kwargs(), precision=precision)
         m.load_state_dict(o.state_dict())
         m = m.to(dev).eval()
         with torch.no_grad():
-            x8 = torch.from_numpy(np.asarray(c.csr[:8].toarray(), dtype=np.float32)).to(dev)
-            s8, mu8, lv8 = m(x8)
+            s8, mu8, lv8 = m(x8c.to(dev))
         # fp32: 768-term dot products in a different summation order, a few 1e-5 absolute on scores of magnitude 1..5;
-        # bf16 mode runs the MLP stack with TF32 operands (10-bit mantissa): 1e-3-level agreement
+        # bf16 mode runs the MLP stack with TF32 operands (10-bit mantissa): 1e-2-level agreement
         rt, at_s, at = (2e-5, 1e-4, 1e-5) if precision == "fp32" else (1e-2, 3e-2, 2e-2)
-        np.testing.assert_allclose(s8.cpu().numpy(), c.z["fwd8/scores"], rtol=rt, atol=at_s)
-        np.testing.assert_allclose(mu8.cpu().numpy(), c.z["fwd8/mu"], rtol=rt, atol=at)
-        np.testing.assert_allclose(lv8.cpu().numpy(), c.z["fwd8/logvar"], rtol=rt, atol=at)
+        np.testing.assert_allclose(s8.cpu().numpy(), os8.numpy(), rtol=rt, atol=at_s)
+        np.testing.assert_allclose(mu8.cpu().numpy(), omu8.numpy(), rtol=rt, atol=at)
+        np.testing.assert_allclose(lv8.cpu().numpy(), olv8.numpy(), rtol=rt, atol=at)
         ev = RecommendationEvaluator(m, c.csr, {}, {}, dev)
         _, idx = ev.topk_users(np.arange(64), 20)
         got = idx.cpu().numpy()
