@@ -18,8 +18,10 @@
 namespace hvae {
 namespace tc {
 
-constexpr int TG_BM = 128, TG_BN = 64, TG_BK = 32, TG_MAX_STAGES = 8;
-constexpr int TG_A_BYTES = TG_BM * TG_BK * 4, TG_B_BYTES = TG_BN * TG_BK * 4, TG_TILES = TG_A_BYTES + TG_B_BYTES;
+// Output tile 128 x BN with BN = 64 (small batches: more CTAs, split-K over a cluster), 128 or 256 (large batches: the TF32 rounding
+// pass over the A tile is amortised over 2-4x more MMA work, one wave of CTAs instead of three).
+constexpr int TG_BM = 128, TG_BK = 32, TG_MAX_STAGES = 8;
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 4;
 // stage = [A tile | B tile | A raw (only if A is MN-major) | B raw (only if B is MN-major)]; as many stages as fit (<= 8)
 constexpr int TG_SMEM_BUDGET = 196608;
 constexpr int TG_CONV_WARPS = 8, TG_THREADS = 64 + 32 * TG_CONV_WARPS;
@@ -28,6 +30,7 @@ struct TGemmParams {
     int M, N, K;
     int a_mn, b_mn;   // 1: operand is MN-major (m resp. n contiguous in memory)
     int stage_bytes, n_stages;
+    int conv_per_stage;   // conversion warps that share one ring stage (8 warps over n_stages stages)
     int ksplit;       // CTAs per output tile (cluster along z): each takes a contiguous range of k-blocks
     int direct;       // debug (HVAE_TF32_TRUNC=1, both operands K-major): skip the rounding pass, the MMA truncates
     float* C;
@@ -50,27 +53,28 @@ __device__ __forceinline__ float rn_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// (All loads of a row are issued before its first store: chunk positions depend on the row index at run time, so the compiler
+// cannot prove that a store does not alias a later load and would otherwise serialise 8 load -> store round trips per row.)
 __device__ __forceinline__ void transpose_to_kmajor(const uint8_t* raw, uint8_t* tile, int x) {
     const float* src = reinterpret_cast<const float*>(raw + (x >> 5) * 4096) + (x & 31);
     uint8_t* dst = tile + x * 128;
+    float v[32];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float4 v;
-        v.x = rn_tf32(src[(4 * c + 0) * 32]); v.y = rn_tf32(src[(4 * c + 1) * 32]);
-        v.z = rn_tf32(src[(4 * c + 2) * 32]); v.w = rn_tf32(src[(4 * c + 3) * 32]);
-        *reinterpret_cast<float4*>(dst + ((c ^ (x & 7)) << 4)) = v;
-    }
+    for (int k = 0; k < 32; ++k) v[k] = src[k * 32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(dst + ((c ^ (x & 7)) << 4)) =
+            make_float4(rn_tf32(v[4 * c]), rn_tf32(v[4 * c + 1]), rn_tf32(v[4 * c + 2]), rn_tf32(v[4 * c + 3]));
 }
 // K-major operand already in place (TMA wrote it swizzled): round its row x in place.
 __device__ __forceinline__ void round_row_inplace(uint8_t* tile, int x) {
     float4* row = reinterpret_cast<float4*>(tile + x * 128);
+    float4 v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int cc = c ^ (x & 7);      // rows are 128 B apart: walk the chunks in swizzled order -> bank-conflict free
-        float4 v = row[cc];
-        v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w);
-        row[cc] = v;
-    }
+    for (int c = 0; c < 8; ++c) v[c] = row[c ^ (x & 7)];     // rows are 128 B apart: chunks in swizzled order -> bank-conflict free
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        row[c ^ (x & 7)] = make_float4(rn_tf32(v[c].x), rn_tf32(v[c].y), rn_tf32(v[c].z), rn_tf32(v[c].w));
 }
 
 // kind::tf32 instruction descriptor: D = f32, A = B = tf32 (format 2), major bits, N>>3, M>>4
@@ -88,8 +92,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
 }
 
+template <int TG_BN>
 __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB, TGemmParams P) {
+    constexpr int TG_B_BYTES = TG_BN * TG_BK * 4, TG_TILES = TG_A_BYTES + TG_B_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int TG_STAGES = P.n_stages, TG_STAGE = P.stage_bytes;
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_c
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < TG_STAGES; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int s = 0; s < TG_STAGES; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->full[s], P.conv_per_stage); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->acc_full, 1);
         fence_barrier_init();
     }
@@ -164,22 +170,26 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32_kernel(const __grid_c
         // round (and, for MN-major operands, transpose) the whole stage into K-major TF32 tiles, lane <-> rows lane+32i.
         // (as many conversion warps as stages take part, so a stage is always served by the same warp: a parity wait
         // on a barrier that is a whole phase behind would otherwise pass immediately)
-        const int cw = warp - 2;
-        for (int kb = cw; kb < KB && cw < TG_STAGES && !P.direct; kb += TG_STAGES) {
+        // stage s is always served by the same g = conv_per_stage warps (a parity wait on a barrier that is a whole phase behind
+        // would pass immediately); they share the stage's 32-row groups (A: BM/32, B: BN/32) round-robin
+        const int cw = warp - 2, g = P.conv_per_stage;
+        const int my_stage = cw / g, part = cw % g;
+        for (int kb = my_stage; kb < KB && my_stage < TG_STAGES && !P.direct; kb += TG_STAGES) {
             const int s = kb % TG_STAGES;
             mbar_wait(&bars->raw_full[s], (kb / TG_STAGES) & 1);
             uint8_t* a = smem + s * TG_STAGE;
 #pragma unroll
-            for (int i = 0; i < TG_BM / 32; ++i) {
-                const int x = lane + 32 * i;
-                if (P.a_mn) transpose_to_kmajor(a + raw_a, a, x);
-                else round_row_inplace(a, x);
-            }
-#pragma unroll
-            for (int i = 0; i < TG_BN / 32; ++i) {
-                const int x = lane + 32 * i;
-                if (P.b_mn) transpose_to_kmajor(a + raw_b, a + TG_A_BYTES, x);
-                else round_row_inplace(a + TG_A_BYTES, x);
+            for (int i = 0; i < TG_BM / 32 + TG_BN / 32; ++i) {
+                if (i % g != part) continue;
+                if (i < TG_BM / 32) {
+                    const int x = lane + 32 * i;
+                    if (P.a_mn) transpose_to_kmajor(a + raw_a, a, x);
+                    else round_row_inplace(a, x);
+                } else {
+                    const int x = lane + 32 * (i - TG_BM / 32);
+                    if (P.b_mn) transpose_to_kmajor(a + raw_b, a + TG_A_BYTES, x);
+                    else round_row_inplace(a + TG_A_BYTES, x);
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -290,6 +300,51 @@ constexpr size_t kTGemmSmem = TG_SMEM_BUDGET + 512 + 1024;
 using namespace hvae;
 using namespace hvae::tc;
 
+// One launch configuration of the templated kernel.
+template <int BN>
+static int launch_gemm_tf32(TGemmParams P, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
+                            int ksplit, cudaStream_t stream) {
+    constexpr int B_BYTES = BN * TG_BK * 4, TILES = TG_A_BYTES + B_BYTES;
+    const int M = P.M, N = P.N, K = P.K;
+    P.stage_bytes = TILES + (P.a_mn ? TG_A_BYTES : 0) + (P.b_mn ? B_BYTES : 0);
+    P.n_stages = min(TG_MAX_STAGES, TG_SMEM_BUDGET / P.stage_bytes);
+    P.conv_per_stage = max(1, TG_CONV_WARPS / P.n_stages);
+    P.ksplit = ksplit;
+    CUtensorMap tmA, tmB;
+    // A(m,k): K-major -> view [M outer, K inner] stride a_rs; MN-major -> view [K outer, M inner] stride a_cs
+    if (int rc = P.a_mn ? make_tmap_f32(&tmA, A, M, K, a_cs, 32, false) : make_tmap_f32(&tmA, A, K, M, a_rs, TG_BM, true)) return rc;
+    // B(k,n): K-major (k contiguous) -> view [N outer, K inner] stride b_cs; MN-major -> view [K outer, N inner] stride b_rs
+    if (int rc = P.b_mn ? make_tmap_f32(&tmB, B, N, K, b_rs, 32, false) : make_tmap_f32(&tmB, B, K, N, b_cs, BN, true)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HVAE_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTGemmSmem));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(N, BN), ceil_div(M, TG_BM), ksplit);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TG_THREADS);
+    cfg.dynamicSmemBytes = kTGemmSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (ksplit > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = ksplit;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    HVAE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN>, tmA, tmB, P));
+    HVAE_LAUNCH_CHECK("gemm_tf32");
+    return 0;
+}
+
 extern "C" {
 
 // 1 if the operands satisfy the TMA constraints of hvae_gemm_tf32 (unit stride on one axis of A and of B, the
@@ -311,53 +366,31 @@ int hvae_gemm_tf32(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_
     P.b_mn = (b_rs == 1) ? 0 : 1;
     if (a_cs == 1 && a_rs == 1) P.a_mn = 0;
     if (b_rs == 1 && b_cs == 1) P.b_mn = 0;
-    P.stage_bytes = TG_TILES + (P.a_mn ? TG_A_BYTES : 0) + (P.b_mn ? TG_B_BYTES : 0);
-    P.n_stages = min(TG_MAX_STAGES, TG_SMEM_BUDGET / P.stage_bytes);
     static const bool trunc = getenv("HVAE_TF32_TRUNC") != nullptr;
     P.direct = (trunc && !P.a_mn && !P.b_mn) ? 1 : 0;
-    CUtensorMap tmA, tmB;
-    // A(m,k): K-major -> view [M outer, K inner] stride a_rs; MN-major -> view [K outer, M inner] stride a_cs
-    if (int rc = P.a_mn ? make_tmap_f32(&tmA, A, M, K, a_cs, 32, false) : make_tmap_f32(&tmA, A, K, M, a_rs, TG_BM, true)) return rc;
-    // B(k,n): K-major (k contiguous) -> view [N outer, K inner] stride b_cs; MN-major -> view [K outer, N inner] stride b_rs
-    if (int rc = P.b_mn ? make_tmap_f32(&tmB, B, N, K, b_rs, 32, false) : make_tmap_f32(&tmB, B, K, N, b_cs, TG_BN, true)) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HVAE_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTGemmSmem));
-        attr_set = true;
-    }
-    dim3 grid(ceil_div(N, TG_BN), ceil_div(M, TG_BM));
-    const int tiles = grid.x * grid.y, KB = ceil_div(K, TG_BK);
     static const bool no_split = getenv("HVAE_NO_SPLITK") != nullptr;
-    P.ksplit = 1;
-    if (!no_split) {
-        // split only while every CTA keeps >= 4 k-blocks (two cluster barriers + the DSMEM reduction cost ~1 us) and the whole
-        // grid stays within one wave (clusters of 4 strand some SMs: stay below 132 CTAs)
-        if (KB >= 16 && tiles * 4 <= 132) P.ksplit = 4;
-        else if (KB >= 8 && tiles * 2 <= 132) P.ksplit = 2;
-    }
-    grid.z = P.ksplit;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(TG_THREADS);
-    cfg.dynamicSmemBytes = kTGemmSmem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (P.ksplit > 1) {
-        attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = P.ksplit;
-        ++na;
-    }
-    if (pdl_enabled()) {
-        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = na;
-    HVAE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel, tmA, tmB, P));
-    HVAE_LAUNCH_CHECK("gemm_tf32");
-    return 0;
+    static const char* force_bn = getenv("HVAE_TF32_BN");
+    const int KB = ceil_div(K, TG_BK), m_tiles = ceil_div(M, TG_BM);
+    // Tile width (measured on B200 at the C2 / C3 shapes, tools/bench_gemm_c3.py): 128 x 64 tiles for small batches (more CTAs,
+    // split-K over a cluster); from 2,048 rows (or k's) on, 128 x 256 when both operands are K-major and N >= 512 (4-stage ring: the
+    // rounding pass over the A tile is shared by 4x the MMA work), 128 x 128 when there are >= 24 such tiles and N >= 384 (an
+    // MN-major operand needs a raw staging area per stage: at 256 columns only 2 stages fit), else 128 x 64.
+    const int big = max(M, K) >= 2048;
+    int best_bn = 64;
+    if (big && !P.a_mn && !P.b_mn && N >= 512) best_bn = 256;
+    else if (big && N >= 384 && m_tiles * ceil_div(N, 128) >= 24) best_bn = 128;
+    if (force_bn) best_bn = atoi(force_bn);
+    HVAE_REQUIRE(best_bn == 64 || best_bn == 128 || best_bn == 256, "gemm_tf32: HVAE_TF32_BN must be 64, 128 or 256");
+    // Split-K over a cluster: a CTA costs ~5.6 us fixed + ~0.4-0.65 us per 32-wide k-block, a split adds ~1 us (two cluster barriers
+    // + the DSMEM reduction); only while every CTA keeps >= 4 k-blocks, the partials fit shared memory and the grid stays in one wave.
+    const int tiles = m_tiles * ceil_div(N, best_bn);
+    const int max_split = no_split ? 1 : min(4, TG_SMEM_BUDGET / (best_bn * TG_BM * 4) + 1);
+    int best_split = 1;
+    if (max_split >= 4 && KB >= 16 && tiles * 4 <= 132) best_split = 4;
+    else if (max_split >= 2 && KB >= 8 && tiles * 2 <= 132) best_split = 2;
+    if (best_bn == 256) return launch_gemm_tf32<256>(P, A, a_rs, a_cs, B, b_rs, b_cs, best_split, (cudaStream_t)stream);
+    if (best_bn == 128) return launch_gemm_tf32<128>(P, A, a_rs, a_cs, B, b_rs, b_cs, best_split, (cudaStream_t)stream);
+    return launch_gemm_tf32<64>(P, A, a_rs, a_cs, B, b_rs, b_cs, best_split, (cudaStream_t)stream);
 }
 
 }  // extern "C"
