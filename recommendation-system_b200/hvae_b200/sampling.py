@@ -30,20 +30,35 @@ def sample_negatives(indptr, indices, n_items, users, tests, n_neg, rng):
     for _ in range(8):
         if todo.size == 0:
             break
+        # vectorised over the rows still short of candidates (a per-row Python loop here cost ~0.5 s per 22k users, i.e. most of
+        # a grid-search configuration's wall time): draw, drop seen / test / already-taken / repeated items, keep draw order
         cand = rng.integers(0, n_items, size=(todo.size, draw), dtype=np.int64)
         k = users[todo, None] * n_items + cand
         pos = np.searchsorted(keys, k)
         seen = (pos < keys.shape[0]) & (keys[np.minimum(pos, keys.shape[0] - 1)] == k)
         bad = seen | (cand == tests[todo, None])
-        for j, row in enumerate(todo):                      # de-duplicate within the row, keep draw order
-            c = cand[j][~bad[j]]
-            _, first = np.unique(c, return_index=True)
-            c = c[np.sort(first)]
-            have = out[row, 1:1 + filled[row]]
-            c = c[~np.isin(c, have)]
-            take = min(n_neg - filled[row], c.shape[0])
-            out[row, 1 + filled[row]:1 + filled[row] + take] = c[:take]
-            filled[row] += take
+        have_n = filled[todo]
+        if have_n.any():                                    # later rounds: not the ones taken in earlier rounds
+            have = out[todo, 1:]
+            for j in range(int(have_n.max())):
+                bad |= (cand == have[:, j:j + 1]) & (j < have_n)[:, None]
+        order = np.argsort(cand, axis=1, kind="stable")     # repeats within the draw: keep the first occurrence
+        srt = np.take_along_axis(cand, order, axis=1)
+        dup_sorted = np.zeros_like(bad)
+        dup_sorted[:, 1:] = srt[:, 1:] == srt[:, :-1]
+        dup = np.zeros_like(bad)
+        np.put_along_axis(dup, order, dup_sorted, axis=1)
+        bad |= dup
+        first_good = np.argsort(bad, axis=1, kind="stable")                 # good candidates first, in draw order
+        n_good = (~bad).sum(axis=1)
+        take = np.minimum(n_neg - have_n, n_good)
+        slots = np.arange(draw)[None, :]
+        sel = slots < take[:, None]
+        picked = np.take_along_axis(cand, first_good, axis=1)
+        rows_rep = np.repeat(todo, take)
+        cols_rep = (1 + have_n)[:, None] + slots
+        out[rows_rep, cols_rep[sel]] = picked[sel]
+        filled[todo] = have_n + take
         todo = todo[filled[todo] < n_neg]
     for row in todo:                                        # tiny catalogues: take everything that is available
         mask = np.ones(n_items, dtype=bool)
@@ -58,13 +73,70 @@ def sample_negatives(indptr, indices, n_items, users, tests, n_neg, rng):
     return out, valid
 
 
-def candidate_ranks(ev, users, cand: np.ndarray):
+def sample_negatives_device(csr, users, tests, n_neg, seed=None):
+    """The same candidate sets drawn ON THE DEVICE (torch index ops: sort / searchsorted): -> (cand int32
+    [n, 1 + n_neg] on the device, valid int32 [n] on the host).  Rows of catalogues too small to yield n_neg unseen items fall
+    back to the host sampler above."""
+    dev = csr.indptr.device
+    N = csr.n_items
+    users_h, tests_h = np.asarray(users, dtype=np.int64), np.asarray(tests, dtype=np.int64)
+    users_d, tests_d = torch.as_tensor(users_h, device=dev), torch.as_tensor(tests_h, device=dev)
+    n = users_d.shape[0]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31 - 1)))
+    keys = getattr(csr, "_pair_keys", None)
+    if keys is None:        # (user, item) pairs as sorted int64 keys; CSR order is already sorted
+        lens = csr.indptr[1:] - csr.indptr[:-1]
+        keys = torch.repeat_interleave(torch.arange(csr.n_users, device=dev, dtype=torch.int64), lens) * N + csr.indices.to(torch.int64)
+        csr._pair_keys = keys
+    out = torch.full((n, 1 + n_neg), -1, dtype=torch.int64, device=dev)
+    out[:, 0] = tests_d
+    filled = torch.zeros(n, dtype=torch.int64, device=dev)
+    todo = torch.arange(n, device=dev)
+    draw = min(n_neg + 32, max(n_neg, N))
+    for _ in range(8):
+        if todo.numel() == 0:
+            break
+        cand = torch.randint(0, N, (todo.numel(), draw), generator=gen, device=dev)
+        k = users_d[todo, None] * N + cand
+        pos = torch.searchsorted(keys, k.reshape(-1)).reshape(k.shape).clamp_(max=max(keys.numel() - 1, 0))
+        bad = (keys[pos] == k) if keys.numel() else torch.zeros_like(k, dtype=torch.bool)
+        bad |= cand == tests_d[todo, None]
+        # repeats: within the draw and against what the row already holds -- stable sort, every later equal value is a repeat
+        have = out[todo, 1:]                                         # -1 in free slots
+        both = torch.cat([have, cand], dim=1)
+        srt, order = torch.sort(both, dim=1, stable=True)
+        dup_sorted = torch.zeros_like(both, dtype=torch.bool)
+        dup_sorted[:, 1:] = srt[:, 1:] == srt[:, :-1]
+        dup = torch.zeros_like(dup_sorted).scatter_(1, order, dup_sorted)
+        bad |= dup[:, n_neg:]
+        good = ~bad
+        rank = torch.cumsum(good, dim=1)                              # 1-based position among the good candidates, draw order
+        need = (n_neg - filled[todo])[:, None]
+        sel = good & (rank <= need)
+        rows = todo[:, None].expand_as(cand)[sel]
+        cols = (filled[todo][:, None] + rank)[sel]                    # slot 1 + filled + (rank - 1)
+        out[rows, cols] = cand[sel]
+        filled[todo] = filled[todo] + sel.sum(dim=1)
+        todo = todo[filled[todo] < n_neg]
+    valid = np.full(n, n_neg, dtype=np.int32)
+    cand32 = out.to(torch.int32)
+    if todo.numel():          # tiny catalogues: the host sampler takes whatever is available for these rows
+        idx = todo.cpu().numpy()
+        hc, hv = sample_negatives(csr.indptr.cpu().numpy(), csr.indices.cpu().numpy(), N, users_h[idx], tests_h[idx], n_neg,
+                                  np.random.default_rng(seed))
+        cand32[todo] = torch.from_numpy(hc).to(dev)
+        valid[idx] = hv
+    return cand32.contiguous(), valid
+
+
+def candidate_ranks(ev, users, cand):
     """0-based rank of candidate 0 among each row's candidates, computed on the device."""
     eng = ev.model.engine
     dev = ev.device
     n, C = cand.shape
     ranks = torch.empty(n, dtype=torch.int32, device=dev)
-    cand_d = torch.from_numpy(np.ascontiguousarray(cand)).to(dev)
+    cand_d = cand.contiguous() if isinstance(cand, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cand)).to(dev)
     users_d = torch.as_tensor(np.asarray(users, dtype=np.int32), device=dev)
     d = eng.lay.d
     with torch.no_grad():
@@ -90,12 +162,8 @@ def evaluate_with_negatives(ev, users, tests, n_negatives, k_values, seed=None, 
         n_negatives = negatives.shape[1]
         cand = np.concatenate([np.asarray(tests, dtype=np.int32)[:, None], negatives], axis=1)
         valid = np.full(cand.shape[0], n_negatives, dtype=np.int32)
-    else:
-        rng = np.random.default_rng(seed)
-        csr = ev._csr
-        indptr = csr.indptr.cpu().numpy()
-        indices = csr.indices.cpu().numpy()
-        cand, valid = sample_negatives(indptr, indices, ev.n_items, users, tests, n_negatives, rng)
+    else:       # drawn on the device (the host sampler `sample_negatives` is the NumPy statement the CPU tests check)
+        cand, valid = sample_negatives_device(ev._csr, users, tests, n_negatives, seed)
     ranks = candidate_ranks(ev, users, cand).astype(np.int64)
     short = valid < n_negatives
     if short.any():       # padded slots repeat the test item (score == test score -> counted as ahead): remove them

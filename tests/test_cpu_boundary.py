@@ -197,3 +197,22 @@ def test_torch_custom_ops_registered_and_cuda_only():
                                               torch.empty(5, dtype=torch.int32), 7, 0)
         assert v.shape == (5, 7) and i.dtype == torch.int32
         assert torch.ops.hvae_b200.gemm(torch.empty(5, 16), torch.empty(9, 16), None, True).shape == (5, 9)
+
+
+def test_device_negative_sampler_on_cpu_tensors():
+    """sampling.sample_negatives_device (torch index ops; runs on any device): test item first, 99 distinct unseen negatives,
+    short catalogues fall back to whatever is available (reference src/ml/evaluate.py:160-172)."""
+    from hvae_b200.engine import DeviceCSR
+    from hvae_b200.sampling import sample_negatives_device
+    from hvae_b200.synth import make_interactions
+    for (U, N) in [(200, 12101), (20, 40)]:
+        d = make_interactions(U, N, 1)
+        csr = DeviceCSR.from_arrays(d.indptr, d.indices, None, N, torch.device("cpu"))
+        cand, valid = sample_negatives_device(csr, np.arange(U), d.test_items, 99, seed=3)
+        cand = cand.numpy()
+        assert cand.shape == (U, 100) and np.array_equal(cand[:, 0], d.test_items)
+        for u in range(U):
+            seen = set(d.indices[d.indptr[u]:d.indptr[u + 1]].tolist())
+            neg = cand[u, 1:1 + valid[u]].tolist()
+            assert len(set(neg)) == len(neg) and not (set(neg) & seen) and d.test_items[u] not in neg
+            assert valid[u] == min(99, N - len(seen) - 1)

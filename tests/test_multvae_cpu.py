@@ -1,6 +1,7 @@
 """CPU: the Mult-VAE restatement (oracle/hvae_oracle.py: OracleMultVAE) against vectors frozen from the reference's own
 MultVAE (oracle/make_golden_multvae.py; src/ml/baseline.py:126-206)."""
 import numpy as np
+import pytest
 import torch
 from scipy.sparse import csr_matrix
 
@@ -24,10 +25,17 @@ def dense_noise(g, csr, s):
                 eps=torch.from_numpy(g[f"noise/{s}/eps"]))
 
 
+@pytest.fixture(autouse=True)
+def _one_thread():
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)          # the golden was frozen with one thread (fixed reduction order)
+    yield
+    torch.set_num_threads(n)
+
+
 def test_multvae_oracle_matches_reference():
     g, csr = load_case()
     n_items, h, L = int(g["n_items"]), int(g["hidden"]), int(g["latent"])
-    torch.set_num_threads(1)
     torch.manual_seed(int(g["seed"]))
     m = orc.OracleMultVAE(n_items, h, L, float(g["dropout"]))
     for k, v in m.state_dict().items():

