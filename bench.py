@@ -194,6 +194,51 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def torch_cuda_eager(c, data, E, dev, steps=5):
+    """Context only (not the baseline, not the product): the reference's module tree (oracle restatement) moved to the GPU, as the
+    reference supports with --device cuda (src/ml/train.py:185-193,360): stock ATen / cuBLAS fp32 kernels on DENSE [B, N] batches
+    (built on the device from the CSR; the reference densifies on the host).  One train step = train.py:88-96."""
+    from oracle import hvae_oracle as orc
+    torch.manual_seed(0)
+    m = orc.OracleVAE(c["n_items"], E, c["latent_dim"], c["hidden_dims"], c["dropout"], c["beta"]).to(dev)
+    opt = orc.make_adam(m)
+    m.train()
+    B, N = c["batch"], c["n_items"]
+    indptr, indices = torch.from_numpy(data.indptr).to(dev), torch.from_numpy(data.indices.astype(np.int64)).to(dev)
+
+    def dense(rows):
+        lens = indptr[rows + 1] - indptr[rows]
+        r = torch.repeat_interleave(torch.arange(rows.numel(), device=dev), lens)
+        starts = torch.repeat_interleave(indptr[rows], lens)
+        off = torch.arange(r.numel(), device=dev) - torch.repeat_interleave(torch.cumsum(lens, 0) - lens, lens)
+        x = torch.zeros(rows.numel(), N, device=dev)
+        x[r, indices[starts + off]] = 1.0
+        return x
+
+    order = torch.from_numpy(np.random.default_rng(0).permutation(c["n_users"])).to(dev)
+    ts = []
+    for s in range(steps + 2):
+        rows = order[s * B:(s + 1) * B]
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        x = dense(rows)
+        opt.zero_grad()
+        sc, mu, lv = m.forward_ref(x)
+        loss, _, _ = orc.loss_terms(sc, x, mu, lv, c["beta"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=5.0)
+        opt.step()
+        loss.item()
+        ts.append(time.perf_counter() - t0)
+    del m, opt
+    gc.collect()
+    torch.cuda.empty_cache()
+    t = float(np.mean(ts[2:]))
+    return {"value": B / t, "unit": UNIT, "ms_per_step": 1e3 * t, "steps": steps, "batch": B,
+            "what": "oracle/hvae_oracle.py (the reference's module tree) on device=cuda: stock ATen/cuBLAS fp32 on dense [B, N] batches, "
+                    "eager, incl. on-device densification and the loss .item(); context for the CPU baseline, not a baseline itself"}
+
+
 # ---- helpers of the b200 arm -------------------------------------------------------------------------------------
 class Ctx:
     pass
@@ -716,6 +761,10 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
+        try:
+            extra["torch_cuda_eager"] = torch_cuda_eager(c_cpu, data_cpu, E_cpu, dev)
+        except Exception as e:       # context number only (e.g. out of memory on a smaller GPU)
+            extra["torch_cuda_eager"] = {"unavailable": str(e)[:200]}
         ref = CpuReference(c_cpu, data_cpu, E_cpu)
         Bs = ref.pick_sample(args.cpu_seconds / 3.0, c_cpu["batch"])
         ref.step(Bs)
