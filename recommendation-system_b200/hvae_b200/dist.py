@@ -156,8 +156,9 @@ class ShardedEvaluator:
             return
         self._graph.replay()
 
-    def topk(self, users: torch.Tensor, out_idx: torch.Tensor = None):
-        """Top-K item ids [n, K] (int32, device) of `users` (device int32 ids; every rank passes the same list)."""
+    def topk(self, users: torch.Tensor, out_idx: torch.Tensor = None, out_val: torch.Tensor = None):
+        """Top-K item ids [n, K] (int32, device) of `users` (device int32 ids; every rank passes the same list); the scores too
+        when `out_val` [n, K] f32 is given."""
         n, T = users.shape[0], self.tile
         out = out_idx if out_idx is not None else torch.empty(n, self.K, dtype=torch.int32, device=self.eng.dev)
         with torch.no_grad():
@@ -165,9 +166,11 @@ class ShardedEvaluator:
                 m = min(T, n - s)
                 self.rows[:m].copy_(users[s:s + m])
                 if m < T:
-                    self.rows[m:].fill_(int(users[0]))      # pad slots repeat a valid user; their results are dropped
+                    self.rows[m:].copy_(users[:1].expand(T - m))      # pad slots repeat a valid user; their results are dropped
                 self.run_tile()
                 out[s:s + m].copy_(self.out_idx[:m])
+                if out_val is not None:
+                    out_val[s:s + m].copy_(self.out_val[:m])
         return out
 
 

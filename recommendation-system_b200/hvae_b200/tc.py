@@ -14,6 +14,7 @@ from ._cabi import p
 from .engine import r4, r8
 
 MAX_K_TC = 128       # K <= 32: register-resident lists in the epilogue; K <= 128: shared-memory lists
+MAX_K_REG = 32
 
 
 def user_vectors_bf16(eng, u, B):
