@@ -15,13 +15,13 @@
 //     (the pair kernel above pushed every P tile through DSMEM).
 // Roles per CTA: warp 0 = TMA producer (its own boxes; completion bytes credited to CTA 0's barriers), warp 1 = MMA issuer
 // (CTA 0 only; both allocate TMEM), warps 2..5 = softmax / epilogue (thread <-> TMEM lane: user = lane & 63, item half = lane >> 6).
-// Ring stage = two [64 x 64] bf16 boxes (16 KB) per CTA: two k-blocks of the CTA's 64 items for G1, two 64-column boxes of a
+// Ring (7 stages) stage = two [64 x 64] bf16 boxes (16 KB) per CTA: two k-blocks of the CTA's 64 items for G1, two 64-column boxes of a
 // 64-item half for G2.  Tensor-pipe order: G1(0), G1(1), G2(0), G1(2), G2(1), ... -- the softmax of tile t hides behind G1(t+1).
 #pragma once
 
 constexpr int D_BOX = 8192;                    // one [64 rows x 64 columns] bf16 box, 128B swizzle
 constexpr int D_STAGE = 2 * D_BOX;
-constexpr int D_STAGES = 6;
+constexpr int D_STAGES = 7;
 constexpr int D_MAXD = 768;                    // 12 resident U boxes; O = 3 groups x 128 TMEM columns
 constexpr int D_UBYTES = (D_MAXD / 64) * D_BOX;
 constexpr int D_PBYTES = 2 * D_BOX;            // P tile [64 users x 128 items] bf16 = two 64-item swizzle atoms
@@ -73,7 +73,7 @@ __device__ __forceinline__ float duo_softmax_row(const float (&v)[2][32], float 
     return ls;
 }
 
-constexpr size_t kDuoSmem = 1024 + D_UBYTES + D_STAGES * D_STAGE + 2 * D_PBYTES + 1024;
+constexpr size_t kDuoSmem = 1024 + D_UBYTES + D_STAGES * D_STAGE + D_PBYTES + 1024;
 
 // TRACE (profiling builds of the same code, hvae_tc_duo_trace): lane 0 of the producer / MMA / first softmax warp accumulates
 // clock64() cycles spent in each of its waits and writes 8 counters per role and CTA to `trace`.
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(192, 1) score_grad_duo_kernel(const __grid_con
     uint8_t* ubuf = smem;
     uint8_t* ring = smem + D_UBYTES;
     uint8_t* pbuf = ring + D_STAGES * D_STAGE;
-    DuoBarriers* bars = reinterpret_cast<DuoBarriers*>(pbuf + 2 * D_PBYTES);
+    DuoBarriers* bars = reinterpret_cast<DuoBarriers*>(pbuf + D_PBYTES);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // (provably warp-uniform)
     const int m_tile = blockIdx.y, split = blockIdx.z;
@@ -249,8 +249,8 @@ __global__ void __launch_bounds__(192, 1) score_grad_duo_kernel(const __grid_con
                         }
                     }
                     if (ti >= 1) {         // G2(ti-1): O += P E_t
-                        const int tj = ti - 1, g = sweep * T + tj, b = g & 1, k = g >> 1;
-                        DUO_TIMED(2, mbar_wait(&bars->p_full[b], k & 1));      // both CTAs' softmax warps have written their P rows
+                        const int tj = ti - 1, g = sweep * T + tj;
+                        DUO_TIMED(2, mbar_wait(&bars->p_full[0], g & 1));      // both CTAs' softmax warps have written their P rows
                         tc_fence_after();
                         for (int ih = 0; ih < 2; ++ih)
                             for (int gq = 0; gq < NG; ++gq) {
@@ -261,14 +261,14 @@ __global__ void __launch_bounds__(192, 1) score_grad_duo_kernel(const __grid_con
                                 if (++rs == D_STAGES) { rs = 0; rph ^= 1; }
                                 tc_fence_after();
                                 if (elect_one()) {
-                                    const uint64_t da = dP + (uint32_t)((b * D_PBYTES + ih * D_BOX) >> 4);
+                                    const uint64_t da = dP + (uint32_t)((ih * D_BOX) >> 4);
                                     const uint64_t db = dRingMN + (uint32_t)((s * D_STAGE) >> 4);
                                     const uint32_t dst = tmem_O + gq * 128;
 #pragma unroll
                                     for (int kk = 0; kk < 4; ++kk)      // K = 16 items per MMA: 32 bytes of a P row, 16 rows of the E box
                                         umma_ss_pair(dst, da + 2 * kk, db + (2048 >> 4) * kk, idesc2, (tj | ih | kk) != 0);
                                     umma_commit_pair(&bars->empty[s], 3);
-                                    if (ih == 1 && gq == NG - 1) umma_commit_pair(&bars->p_free[b], 3);
+                                    if (ih == 1 && gq == NG - 1) umma_commit_pair(&bars->p_free[0], 3);
                                 }
                                 __syncwarp();
                             }
@@ -292,15 +292,16 @@ __global__ void __launch_bounds__(192, 1) score_grad_duo_kernel(const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(sfree0 + b * 8);
-                DUO_TIMED(1, mbar_wait(&bars->p_free[b], (k & 1) ^ 1));
+                // ONE P buffer: G2(t-1), which reads it, is issued before G1(t+1), and this store happens while G1(t+1) runs
+                DUO_TIMED(1, mbar_wait(&bars->p_free[0], (g & 1) ^ 1));
                 // my 64 items = one 128-byte row of swizzle atom `half` of the P tile
-                uint8_t* prow = pbuf + b * D_PBYTES + half * D_BOX + u_local * 128;
+                uint8_t* prow = pbuf + half * D_BOX + u_local * 128;
                 const int n_valid = P.N - (t0 + ti) * G_BN - half * 64;      // of my 64 items (TMA zero-fills the rows beyond N)
                 if (n_valid >= 64) lsum += duo_softmax_row<false>(v, shift2, 64, prow, u_local);
                 else lsum += duo_softmax_row<true>(v, shift2, n_valid, prow, u_local);
                 fence_proxy_async();           // my P row (own shared memory) is visible to the MMA's async proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive_remote(pfull0 + b * 8);
+                if (lane == 0) mbar_arrive_remote(pfull0);
             }
             DUO_TIMED(2, mbar_wait(&bars->o_full, sweep & 1));      // every MMA of the sweep has completed
             tc_fence_after();
