@@ -101,13 +101,14 @@ class ShardedEvaluator:
 
     With world == 1 the two collectives drop out.  bf16 mode only (the fp32 path materialises scores: see sharded_topk)."""
 
-    def __init__(self, eng, csr, K: int, group=None, tile: int = 4096, use_graph: bool = True):
+    def __init__(self, eng, csr, K: int, group=None, tile: int = 4096, use_graph: bool = True, sharded: bool = True):
         from . import tc
         if eng.precision == "fp32" or K > tc.MAX_K_TC:
             raise RuntimeError("ShardedEvaluator runs the fused bf16 top-K kernel (K <= %d); use sharded_topk otherwise" % tc.MAX_K_TC)
         self.eng, self.csr, self.K, self.group = eng, csr, K, group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # sharded=False: this rank scores the whole catalogue for its own users (user-sharded evaluation, or a single GPU)
+        self.world = dist.get_world_size(group) if (sharded and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if (sharded and dist.is_initialized()) else 0
         self.tile = (tile + self.world - 1) // self.world * self.world
         self.shard = ItemShard(eng.lay.N, self.world, self.rank)
         dev, T = eng.dev, self.tile

@@ -82,14 +82,13 @@ class RecommendationEvaluator:
         users = torch.as_tensor(np.asarray(user_indices, dtype=np.int32), device=self.device)
         eng = self.model.engine
         from . import tc
-        if (eng.precision != "fp32" and exclude_seen and top_k <= tc.MAX_K_REG and users.shape[0] >= 2 * self.batch_users
-                and not (torch.distributed.is_available() and torch.distributed.is_initialized())):
+        if eng.precision != "fp32" and exclude_seen and top_k <= tc.MAX_K_REG and users.shape[0] >= 2 * self.batch_users:
             # long user lists: the tile (encoder -> fused GEMM + seen mask + top-K -> merge) is captured once as a CUDA graph and
             # replayed per tile (dist.ShardedEvaluator with a single shard), instead of ~15 eager launches per tile
             key = lambda: (top_k, self.batch_users, eng.arena.data_ptr(), eng.E_bf16.data_ptr(), eng.ws.generation)
             if getattr(self, "_tile_key", None) != key():
                 from .dist import ShardedEvaluator
-                self._tile_eval, self._tile_key = ShardedEvaluator(eng, self._csr, top_k, tile=self.batch_users), None
+                self._tile_eval, self._tile_key = ShardedEvaluator(eng, self._csr, top_k, tile=self.batch_users, sharded=False), None
             out_v = torch.empty(users.shape[0], top_k, dtype=torch.float32, device=self.device)
             out_i = self._tile_eval.topk(users, None, out_v)
             self._tile_key = key()          # (after the first tile: it may have grown the workspace the captured graph points into)
