@@ -101,6 +101,35 @@ def _worker(rank, world, port, out_dir):
             seen += rows_step
         assert sorted(seen) == list(range(47))
 
+        # --- the packed (value | id) candidate blocks of ShardedEvaluator: one all-gather of [2, B, K] per rank, merged in place
+        #     with group stride 2*B*K (what hvae_topk_merge_groups reads) == the merge of the concatenated candidates
+        send = torch.empty(2, B, K, dtype=torch.int32)
+        send[0] = torch.from_numpy(lv).view(torch.int32)
+        send[1] = torch.from_numpy(li)
+        recv = torch.empty(world * 2, B, K, dtype=torch.int32)    # == [rank][2][B][K]
+        dist.all_gather_into_tensor(recv, send)
+        flat = recv.reshape(-1).numpy()
+        gv = np.stack([np.concatenate([flat[g * 2 * B * K + b * K:g * 2 * B * K + b * K + K].view(np.float32) for g in range(world)])
+                       for b in range(B)])
+        gi = np.stack([np.concatenate([flat[g * 2 * B * K + B * K + b * K:g * 2 * B * K + B * K + b * K + K] for g in range(world)])
+                       for b in range(B)])
+        mv2, mi2 = hd.merge_candidates_host(gv, gi, K)
+        assert np.array_equal(mi2, mi) and np.array_equal(mv2, mv)
+
+        # --- the gradient-exchange path is decided once and collectively: no symmetric memory on CPU -> every rank says "nccl"
+        class _Eng:
+            dev = torch.device("cpu")
+            class ws:
+                generation = 0
+        assert dp.prepare_exchange(_Eng(), 1024) == "nccl" and dp.exchange == "nccl"
+        forced = hd.DataParallel()
+        forced.exchange_mode = "nvl"
+        try:
+            forced.prepare_exchange(_Eng(), 1024)
+            raise AssertionError("HVAE_DP_EXCHANGE=nvl must not fall back silently")
+        except RuntimeError as e:
+            assert "symmetric memory" in str(e)
+
         # --- independent trainings (grid sweep): every configuration placed exactly once
         mine_cfg = hd.assign_round_robin(16, world, rank)
         allc = [None] * world
