@@ -116,6 +116,30 @@ size_t hvae_gemm_tf32_supported(const float* A, int64_t a_rs, int64_t a_cs, cons
 int hvae_gemm_tf32(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
                    int64_t b_cs, float* C, int64_t ldc, const float* bias, float alpha, void* stream);
 
+/* The same tensor-core GEMM with the element-wise kernel that follows it in the model folded into its epilogue (one launch and one
+ * round trip through HBM less each), and the bias gradient (column sums of what the epilogue wrote) added up in a fixed order by
+ * the last m tile to finish.  `workspace`: hvae_gemm_colsum_workspace_floats(M, cols) floats, ZERO before the first use (the kernel
+ * leaves its counters zero); `colsum` may be NULL.
+ *   gelu_drop : pre = A B + bias ; act = gelu(pre) * mask * keep_scale          (model.py:90-93 projection_layer.0-2; ldc for both,
+ *               columns N..ldc-1 are written as zeros)
+ *   bf16      : C = A B + bias (C may be NULL) and its bf16 copy [M, ld_bf16] with zero padding (the user vectors that feed the
+ *               scoring kernels, model.py:94,198)
+ *   gelu_bwd  : dpre = (A B) * mask * keep_scale * gelu'(pre) ; colsum[n] = sum_m dpre[m, n]       (autograd of model.py:90-93)
+ *   latent_bwd: dz = A B [M, L] -> dml = [dz + coef*mu | dz*eps*0.5*exp(0.5 logvar) + coef*0.5*(exp(logvar)-1)], colsum [2L]
+ *               (autograd of model.py:157-179 + the KL term of model.py:286-287; same arithmetic as hvae_latent_bwd) */
+size_t hvae_gemm_colsum_workspace_floats(int M, int cols);
+int hvae_gemm_tf32_gelu_drop(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                             int64_t b_cs, float* pre, float* act, int64_t ldc, const float* bias, const uint8_t* mask,
+                             float keep_scale, void* stream);
+int hvae_gemm_tf32_bf16(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                        int64_t b_cs, float* C, int64_t ldc, const float* bias, void* C_bf16, int64_t ld_bf16, void* stream);
+int hvae_gemm_tf32_gelu_bwd(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                            int64_t b_cs, float* dpre, int64_t ldc, const float* pre, const uint8_t* mask, float keep_scale,
+                            float* colsum, float* workspace, void* stream);
+int hvae_gemm_tf32_latent_bwd(int M, int L, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                              int64_t b_cs, const float* ml, int64_t ldml, const float* eps, const float* coef, float* dml,
+                              float* colsum, float* workspace, void* stream);
+
 /* ---- latent (model.py:157-179, 92-93, 281-290) -------------------------------------------------------- */
 int hvae_reparam_kl(const float* ml, int ldml, const float* eps, int B, int L, float* z, int ldz, float* kl_row,
                     void* stream);
@@ -141,6 +165,12 @@ int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const fl
 int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
                      const float* O, int ldo, int n_parts, const float* oscale, const float* w_part, const void* E, int lde,
                      int d, int is_bf16, const float* inv_bg, float* dU, int lddu, void* stream);
+/* The same directly after hvae_tc_score_onepass, with hvae_tc_onepass_combine folded in (one launch less on the step's critical
+ * path): c_part [n_parts, B], l_part [n_parts, n_sub, B] are the kernel's per-split shifts and numerator sums; writes lse [B]. */
+int hvae_du_finalize_onepass(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B,
+                             const float* O, int ldo, int n_parts, const float* oscale, const float* c_part,
+                             const float* l_part, int n_sub, float* lse, const void* E, int lde, int d, int is_bf16,
+                             const float* inv_bg, float* dU, int lddu, void* stream);
 /* Seen-item masking (in place) + top-K of materialised scores under the order (score desc, index desc).  Rows are cut into
  * hvae_mask_topk_chunks(n_rows, N) column chunks; cand_val / cand_idx: scratch [n_rows, chunks * K] (NULL if chunks == 1). */
 size_t hvae_mask_topk_chunks(int n_rows, int N);
@@ -217,6 +247,11 @@ int hvae_step_begin(hvae_step_state* state, double lr, double beta1, double beta
                     int anneal_steps, int b_global, int advance, uint32_t noise_stride, void* stream);
 int hvae_grad_norm_clip(const float* gdense, int64_t n_dense, const float* rownorm2, const int32_t* n_unique,
                         float max_norm, hvae_step_state* state, float* workspace, void* stream);
+/* The same in two calls (identical arithmetic): the sum of squares of the dense gradients depends on them only and can run beside
+ * the layer-1 weight-gradient kernels; the finish adds the rows' squared norms and writes the clip coefficient. */
+int hvae_grad_sumsq_dense(const float* gdense, int64_t n_dense, float* workspace, void* stream);
+int hvae_grad_norm_finish(int64_t n_dense, const float* rownorm2, const int32_t* n_unique, float max_norm,
+                          hvae_step_state* state, const float* workspace, void* stream);
 int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_params, int64_t n_w1, int ld1,
                    const int32_t* slot_of_item, const float* gsparse, const float* gdense, const hvae_step_state* state,
                    float weight_decay, float beta1, float beta2, float eps, void* stream);

@@ -206,6 +206,23 @@ int hvae_grad_norm_clip(const float* gdense, int64_t n_dense, const float* rowno
     return 0;
 }
 
+// The two halves of hvae_grad_norm_clip as separate calls: the dense part only needs the dense gradients, so a captured step runs it
+// beside the layer-1 weight-gradient kernels instead of after them.  workspace >= 149 floats (partials, then their count).
+int hvae_grad_sumsq_dense(const float* gdense, int64_t n_dense, float* workspace, void* stream) {
+    const int blocks = (int)max((int64_t)1, min((int64_t)kNumSMs, (n_dense + 255) / 256));
+    launch_pdl(sumsq_partial_kernel, blocks, 256, 0, (cudaStream_t)stream, gdense, n_dense, workspace);
+    HVAE_LAUNCH_CHECK("grad_sumsq_dense");
+    return 0;
+}
+
+int hvae_grad_norm_finish(int64_t n_dense, const float* rownorm2, const int32_t* n_unique, float max_norm, hvae_step_state* state,
+                          const float* workspace, void* stream) {
+    const int blocks = (int)max((int64_t)1, min((int64_t)kNumSMs, (n_dense + 255) / 256));
+    launch_pdl(gradnorm_final_kernel, 1, 1024, 0, (cudaStream_t)stream, workspace, blocks, rownorm2, n_unique, max_norm, state);
+    HVAE_LAUNCH_CHECK("grad_norm_finish");
+    return 0;
+}
+
 int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_params, int64_t n_w1, int ld1,
                    const int32_t* slot_of_item, const float* gsparse, const float* gdense, const hvae_step_state* state,
                    float weight_decay, float beta1, float beta2, float eps, void* stream) {

@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restr
                                                           const float* __restrict__ O, int ldo, int n_parts,
                                                           const float* __restrict__ oscale, const float* __restrict__ w_part,
                                                           const T* __restrict__ E, int lde, int d,
-                                                          const float* __restrict__ inv_bg, float* __restrict__ dU, int lddu) {
+                                                          const float* __restrict__ inv_bg, float* __restrict__ dU, int lddu,
+                                                          const float* __restrict__ c_part, const float* __restrict__ l_part, int n_sub,
+                                                          float* __restrict__ lse_out) {
     pdl_prologue();
     const int ld4 = lddu >> 2;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,6 +114,36 @@ __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restr
     const int b = t / ld4, c = (t - b * ld4) * 4;
     const int u = rows ? rows[b] : b;
     const float ib = *inv_bg, s = oscale ? oscale[b] * ib : 1.0f;
+    // One-pass scoring (c_part != null): the combination of the per-split results of this row (shift c_p, numerator sums l_p) is done
+    // here instead of in a launch of its own -- M = max_p c_p, D = sum_p e^{c_p - M} l_p, weight of split p = e^{c_p - M} / D,
+    // lse = M + log D (every thread of a row repeats the few dozen operations; the addresses are warp-uniform)
+    float cM = 0.f, cinv = 1.f;
+    if (c_part) {
+        cM = -INFINITY;
+        for (int p0 = 0; p0 < n_parts; p0 += 8) {          // eight loads in flight (a dependent load per iteration costs ~0.2 us each)
+            float cc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cc[k] = p0 + k < n_parts ? c_part[(size_t)(p0 + k) * B + b] : -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cM = fmaxf(cM, cc[k]);
+        }
+        float D = 0.f;
+        for (int p0 = 0; p0 < n_parts; p0 += 8) {
+            float cc[8], ll[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = p0 + k < n_parts;
+                cc[k] = ok ? c_part[(size_t)(p0 + k) * B + b] : -INFINITY;
+                ll[k] = 0.f;
+                for (int sb = 0; sb < n_sub; ++sb) ll[k] += ok ? l_part[((size_t)(p0 + k) * n_sub + sb) * B + b] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (p0 + k < n_parts) D = fmaf(expf(cc[k] - cM), ll[k], D);
+        }
+        cinv = 1.0f / D;
+        if (c == 0 && lse_out) lse_out[b] = cM + logf(D);
+    }
     const size_t pstride = (size_t)B * ldo;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* op = O + (size_t)b * ldo + c;
@@ -122,7 +154,7 @@ __global__ void __launch_bounds__(256) du_finalize_kernel(const int64_t* __restr
         for (int q = 0; q < 4; ++q) {
             const bool ok = p0 + q < n_parts;
             v[q] = ok ? *reinterpret_cast<const float4*>(op + (size_t)(p0 + q) * pstride) : make_float4(0.f, 0.f, 0.f, 0.f);
-            w[q] = (ok && w_part) ? w_part[(size_t)(p0 + q) * B + b] : 1.0f;
+            w[q] = !ok ? 1.0f : c_part ? expf(c_part[(size_t)(p0 + q) * B + b] - cM) * cinv : w_part ? w_part[(size_t)(p0 + q) * B + b] : 1.0f;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -561,20 +593,38 @@ int hvae_sparse_dot_xsum(const int64_t* indptr, const int32_t* indices, const fl
     return 0;
 }
 
-int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B, const float* O,
-                     int ldo, int n_parts, const float* oscale, const float* w_part, const void* E, int lde, int d, int is_bf16,
-                     const float* inv_bg, float* dU, int lddu, void* stream) {
+static int du_finalize_launch(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B, const float* O,
+                              int ldo, int n_parts, const float* oscale, const float* w_part, const void* E, int lde, int d, int is_bf16,
+                              const float* inv_bg, float* dU, int lddu, const float* c_part, const float* l_part, int n_sub, float* lse,
+                              void* stream) {
     if (B == 0) return 0;
     HVAE_REQUIRE(lddu % 4 == 0 && ldo % 4 == 0 && (!is_bf16 || lde % 8 == 0), "du_finalize: leading dimensions must be multiples of 4 (bf16 E: 8)");
     const int nb = ceil_div(B * (lddu / 4), 256);
     if (is_bf16)
-        launch_pdl(du_finalize_kernel<__nv_bfloat16>, nb, 256, 0, (cudaStream_t)stream, 
-            indptr, indices, values, rows, B, O, ldo, n_parts, oscale, w_part, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu);
+        launch_pdl(du_finalize_kernel<__nv_bfloat16>, nb, 256, 0, (cudaStream_t)stream, indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
+                   w_part, (const __nv_bfloat16*)E, lde, d, inv_bg, dU, lddu, c_part, l_part, n_sub, lse);
     else
         launch_pdl(du_finalize_kernel<float>, nb, 256, 0, (cudaStream_t)stream, indptr, indices, values, rows, B, O, ldo, n_parts, oscale,
-                   w_part, (const float*)E, lde, d, inv_bg, dU, lddu);
+                   w_part, (const float*)E, lde, d, inv_bg, dU, lddu, c_part, l_part, n_sub, lse);
     HVAE_LAUNCH_CHECK("du_finalize");
     return 0;
+}
+
+int hvae_du_finalize(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B, const float* O,
+                     int ldo, int n_parts, const float* oscale, const float* w_part, const void* E, int lde, int d, int is_bf16,
+                     const float* inv_bg, float* dU, int lddu, void* stream) {
+    return du_finalize_launch(indptr, indices, values, rows, B, O, ldo, n_parts, oscale, w_part, E, lde, d, is_bf16, inv_bg, dU, lddu, nullptr,
+                              nullptr, 0, nullptr, stream);
+}
+
+// The same after the one-pass scoring kernel, with hvae_tc_onepass_combine folded in: the weights of the O partial sums come
+// straight from the kernel's per-split shifts c_part [n_parts, B] and numerator sums l_part [n_parts, n_sub, B]; lse [B] is written too.
+int hvae_du_finalize_onepass(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows, int B, const float* O,
+                             int ldo, int n_parts, const float* oscale, const float* c_part, const float* l_part, int n_sub, float* lse,
+                             const void* E, int lde, int d, int is_bf16, const float* inv_bg, float* dU, int lddu, void* stream) {
+    HVAE_REQUIRE(c_part && l_part && n_sub >= 1, "du_finalize_onepass: the one-pass kernel's partial results are required");
+    return du_finalize_launch(indptr, indices, values, rows, B, O, ldo, n_parts, oscale, nullptr, E, lde, d, is_bf16, inv_bg, dU, lddu, c_part,
+                              l_part, n_sub, lse, stream);
 }
 
 int hvae_candidate_rank(const void* U, int ldu, const void* E, int lde, int d, int is_bf16, const int32_t* cand, int C, int B,

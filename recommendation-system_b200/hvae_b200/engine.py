@@ -219,6 +219,7 @@ class _Span:
 
 class Engine:
     ADAM_B1, ADAM_B2, ADAM_EPS, MAX_NORM = 0.9, 0.999, 1e-8, 5.0
+    FUSE_DEFAULT = 0      # measured (profiles/r02_ncu_summary.md section 7): every fusion lengthens the captured step
 
     def __init__(self, layout: Layout, arena: torch.Tensor, E: torch.Tensor, dropout: float, precision: str = "fp32"):
         if not arena.is_cuda:
@@ -236,6 +237,12 @@ class Engine:
         self.slot_of_item = None
         self.dist = None  # set by hvae_b200.dist for data-parallel training
         self._E_bf16 = None
+        # bf16 mode: GELU/dropout, the bf16 cast of u, the latent backward and the bias-gradient column sums ride in GEMM epilogues
+        # HVAE_FUSE: bit mask of the fusions (1 GELU+dropout forward, 2 bf16 copy of u, 4 GELU backward, 8 latent backward, 16 bias-gradient
+        # column sums inside those epilogues, 32 one-pass split combination inside du_finalize)
+        self.fuse = 0 if precision == "fp32" else int(os.environ.get("HVAE_FUSE", str(self.FUSE_DEFAULT)))
+        self.ub_fresh = None
+        self._loss_pending = None
         self.two_pass = os.environ.get("HVAE_TWO_PASS", "0") == "1"   # bf16 training: forward-LSE + backward launches instead of the one-pass kernel
         self.prof = None  # dict name -> [(start, stop) events] when profiling spans are enabled
         self.concurrent, self._side, self._forked = False, [], set()
@@ -373,9 +380,19 @@ class Engine:
             return z
         q, t, u = ws.get("q", (B, ldd)), ws.get("t", (B, ldd)), ws.get("u", (B, ldd))
         w0, w3 = lay.slots["projection_layer.0.weight"], lay.slots["projection_layer.3.weight"]
-        self.mm(B, d, L, p(z), ldz, 1, self.P("projection_layer.0.weight"), 1, w0.ld, p(q), ldd, self.P("projection_layer.0.bias"))
-        lib.gelu_drop_fwd(p(q), p(pmask), self.keep_scale, B, d, ldd, p(t), st)
-        self.mm(B, d, d, p(t), ldd, 1, self.P("projection_layer.3.weight"), 1, w3.ld, p(u), ldd, self.P("projection_layer.3.bias"))
+        if self.fuse & 1:        # GELU + dropout in the epilogue of the GEMM
+            lib.gemm_tf32_gelu_drop(B, d, L, p(z), ldz, 1, self.P("projection_layer.0.weight"), 1, w0.ld, p(q), p(t), ldd,
+                                    self.P("projection_layer.0.bias"), p(pmask), self.keep_scale, st)
+        else:
+            self.mm(B, d, L, p(z), ldz, 1, self.P("projection_layer.0.weight"), 1, w0.ld, p(q), ldd, self.P("projection_layer.0.bias"))
+            lib.gelu_drop_fwd(p(q), p(pmask), self.keep_scale, B, d, ldd, p(t), st)
+        if self.fuse & 2:        # the bf16 copy of u (operand of the scoring kernels) written by the epilogue
+            ub = ws.get("u_bf16", (B, r8(d)), torch.bfloat16)
+            lib.gemm_tf32_bf16(B, d, d, p(t), ldd, 1, self.P("projection_layer.3.weight"), 1, w3.ld, p(u), ldd,
+                               self.P("projection_layer.3.bias"), p(ub), r8(d), st)
+            self.ub_fresh = (u.data_ptr(), B)        # consumed (once) by tc.user_vectors_bf16
+        else:
+            self.mm(B, d, d, p(t), ldd, 1, self.P("projection_layer.3.weight"), 1, w3.ld, p(u), ldd, self.P("projection_layer.3.bias"))
         return u
 
     def scores_dense(self, u, B, out=None):
@@ -432,9 +449,15 @@ class Engine:
         with self.span("score"):
             lse, dot, xsum, O, oscale = self.score_loss(batch, u, want_grad)
         self.join()
-        with self.side(1):          # nothing downstream of the loss scalars inside the step: off the critical path
-            self.lib.loss_finalize(p(lse), p(dot), p(xsum), p(self.ws.get("kl_row", (batch.B,))), batch.B, self.state_ptr("inv_bg"),
-                                   self.state_ptr("beta_kl"), p(self.loss_out), p(self.acc) if accumulate else None, self.stream)
+
+        def finalize():
+            with self.side(1):          # nothing downstream of the loss scalars inside the step: off the critical path
+                self.lib.loss_finalize(p(lse), p(dot), p(xsum), p(self.ws.get("kl_row", (batch.B,))), batch.B, self.state_ptr("inv_bg"),
+                                       self.state_ptr("beta_kl"), p(self.loss_out), p(self.acc) if accumulate else None, self.stream)
+        if isinstance(oscale, tuple) and len(oscale) == 3:
+            self._loss_pending = finalize       # lse comes out of du_finalize_onepass (first kernel of backward())
+        else:
+            finalize()
         return ml, u, O, oscale
 
     def backward(self, batch: Batch, noise, ml, O, oscale, dense_w1=None, ext_dml=None, du_override=None):
@@ -448,6 +471,8 @@ class Engine:
         pmask = None if noise is None else noise.get("pmask")
         cs_ws = ws.get("colsum_ws", (64 * max(max(h), 2 * L, d) + 64,))     # side stream 1 only
         cs_ws2 = cs_ws                                                      # (same stream -> same scratch is safe)
+        fuse = self.fuse if ext_dml is None else 0
+        f_gelu, f_lat, f_cs = bool(fuse & 4), bool(fuse & 8) and not lay.identity_proj, bool(fuse & 16)
         if du_override is not None:
             dU = du_override
         else:
@@ -455,9 +480,16 @@ class Engine:
             is_bf16 = 0 if self.precision == "fp32" else 1
             Eg, lde = (self.E, d) if not is_bf16 else (self.E_bf16, r8(d))
             n_parts = O.shape[0] if O.dim() == 3 else 1
-            oscale, w_part = oscale if isinstance(oscale, tuple) else (oscale, None)
-            lib.du_finalize(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(O), ldd, n_parts, p(oscale), p(w_part),
-                            p(Eg), lde, d, is_bf16, self.state_ptr("inv_bg"), p(dU), ldd, st)
+            if isinstance(oscale, tuple) and len(oscale) == 3:       # one-pass scoring: the split combination rides in this kernel
+                oscale, (c_part, l_part, n_sub), lse = oscale
+                lib.du_finalize_onepass(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(O), ldd, n_parts, p(oscale),
+                                        p(c_part), p(l_part), n_sub, p(lse), p(Eg), lde, d, is_bf16, self.state_ptr("inv_bg"), p(dU), ldd, st)
+                self._loss_pending()
+                self._loss_pending = None
+            else:
+                oscale, w_part = oscale if isinstance(oscale, tuple) else (oscale, None)
+                lib.du_finalize(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(O), ldd, n_parts, p(oscale), p(w_part),
+                                p(Eg), lde, d, is_bf16, self.state_ptr("inv_bg"), p(dU), ldd, st)
         if lay.identity_proj:
             dz = dU
         else:
@@ -468,19 +500,33 @@ class Engine:
                 self.mm(d, d, B, p(dU), 1, ldd, p(t), ldd, 1, self.G("projection_layer.3.weight"), w3.ld)
             with self.side(1):
                 lib.colsum(p(dU), ldd, B, d, self.G("projection_layer.3.bias"), p(cs_ws), self.stream)
-            dt = ws.get("dt", (B, ldd))
-            self.mm(B, d, d, p(dU), ldd, 1, self.P("projection_layer.3.weight"), w3.ld, 1, p(dt), ldd)
             dq = ws.get("dq", (B, ldd))
-            lib.gelu_drop_bwd(p(dt), p(q), p(pmask), self.keep_scale, B, d, ldd, p(dq), st)
+            if f_gelu:
+                # dq = (dU Wp3) * dropout * gelu'(q) (and its column sums = d bias of projection_layer.0) in one launch
+                lib.gemm_tf32_gelu_bwd(B, d, d, p(dU), ldd, 1, self.P("projection_layer.3.weight"), w3.ld, 1, p(dq), ldd, p(q), p(pmask),
+                                       self.keep_scale, self.G("projection_layer.0.bias") if f_cs else None,
+                                       p(self._colsum_ws("dq", B, d)) if f_cs else None, st)
+            else:
+                dt = ws.get("dt", (B, ldd))
+                self.mm(B, d, d, p(dU), ldd, 1, self.P("projection_layer.3.weight"), w3.ld, 1, p(dt), ldd)
+                lib.gelu_drop_bwd(p(dt), p(q), p(pmask), self.keep_scale, B, d, ldd, p(dq), st)
+            if not (f_gelu and f_cs):
+                with self.side(1):
+                    lib.colsum(p(dq), ldd, B, d, self.G("projection_layer.0.bias"), p(cs_ws2), self.stream)
             with self.side(0):
                 self.mm(d, L, B, p(dq), 1, ldd, p(z), ldz, 1, self.G("projection_layer.0.weight"), w0.ld)
-            with self.side(1):
-                lib.colsum(p(dq), ldd, B, d, self.G("projection_layer.0.bias"), p(cs_ws2), self.stream)
-            dz = ws.get("dz", (B, ldz))
-            self.mm(B, L, d, p(dq), ldd, 1, self.P("projection_layer.0.weight"), w0.ld, 1, p(dz), ldz)
+            if not f_lat:
+                dz = ws.get("dz", (B, ldz))
+                self.mm(B, L, d, p(dq), ldd, 1, self.P("projection_layer.0.weight"), w0.ld, 1, p(dz), ldz)
         dml = ws.get("dml", (B, ldml))
-        lib.latent_bwd(p(dz), ldz, p(ml), ldml, p(eps), B, L, self.state_ptr("kl_coef") if ext_dml is None else p(self._zero()),
-                       p(dml), st)
+        if f_lat:
+            # dz = dq Wp0 never leaves the chip: the epilogue turns it into [dmu | dlogvar] (+ KL gradient) (and sums the columns)
+            lib.gemm_tf32_latent_bwd(B, L, d, p(dq), ldd, 1, self.P("projection_layer.0.weight"), w0.ld, 1, p(ml), ldml, p(eps),
+                                     self.state_ptr("kl_coef"), p(dml), self.G("fc_ml.bias") if f_cs else None,
+                                     p(self._colsum_ws("dml", B, 2 * L)) if f_cs else None, st)
+        else:
+            lib.latent_bwd(p(dz), ldz, p(ml), ldml, p(eps), B, L, self.state_ptr("kl_coef") if ext_dml is None else p(self._zero()),
+                           p(dml), st)
         if ext_dml is not None:
             dml[:, :2 * L].add_(ext_dml)
         wm = lay.slots["fc_mu.weight"]
@@ -488,8 +534,9 @@ class Engine:
         act_last = ws.get(f"act{nh - 1}", (B, r4(h[-1])))
         with self.side(0):
             self.mm(2 * L, h[-1], B, p(dml), 1, ldml, p(act_last), r4(h[-1]), 1, self.G("fc_mu.weight"), wm.ld)
-        with self.side(1):
-            lib.colsum(p(dml), ldml, B, 2 * L, self.G("fc_ml.bias"), p(cs_ws), self.stream)
+        if not (f_lat and f_cs):
+            with self.side(1):
+                lib.colsum(p(dml), ldml, B, 2 * L, self.G("fc_ml.bias"), p(cs_ws), self.stream)
         dact = ws.get(f"dact{nh - 1}", (B, r4(h[-1])))
         self.mm(B, h[-1], 2 * L, p(dml), ldml, 1, self.P("fc_mu.weight"), wm.ld, 1, p(dact), r4(h[-1]))
         ln_ws = ws.get("ln_ws", (max(lib.ln_bwd_workspace_floats(B, r4(hh)) for hh in h),))
@@ -512,6 +559,10 @@ class Engine:
         self.dpre0 = dact
         if dense_w1 is not None:
             lib.w1_grad_dense(p(csr.indptr), p(csr.indices), p(csr.values), p(batch.rows), B, p(dact), r4(h[0]), h[0], p(dense_w1), st)
+
+    def _colsum_ws(self, name, B, cols):
+        """Zero-initialised workspace of the column sums a fused GEMM epilogue produces (the kernel leaves its counters zero)."""
+        return self.ws.get("gemm_colsum_" + name, (int(self.lib.gemm_colsum_workspace_floats(B, cols)),), zero=True)
 
     def _zero(self):
         return self.ws.get("zero1", (1,), zero=True)
@@ -588,11 +639,14 @@ class Engine:
         if self.dist is not None:
             with self.span("exchange"):
                 dpre_ptr, block_rows, block_stride = self.dist.exchange_grads(self, batch, self.dpre0)
+        gn_ws = self.ws.get("gn_ws", (256,))
+        with self.side(1):           # the dense gradients are final: their sum of squares runs beside the layer-1 gradient kernels
+            lib.grad_sumsq_dense(p(self.gd), lay.n_dense, p(gn_ws), self.stream)
         with self.span("w1grad"):
             gs, rn2 = self.w1_grad(tb, dpre_ptr, block_rows, block_stride)
         n_unique, uniq = tb["n_unique"], tb["uniq"]
-        gn_ws = self.ws.get("gn_ws", (256,))
-        lib.grad_norm_clip(p(self.gd), lay.n_dense, p(rn2), p(n_unique), self.MAX_NORM, p(self.state), p(gn_ws), st)
+        self.join(only=(1,))
+        lib.grad_norm_finish(lay.n_dense, p(rn2), p(n_unique), self.MAX_NORM, p(self.state), p(gn_ws), st)
         with self.span("adam"):
             lib.adam_step(p(self.arena), p(self.m), p(self.v), lay.n_params, lay.n_w1, r4(lay.hidden[0]), p(self.slot_of_item), p(gs),
                           p(self.gd), p(self.state), weight_decay, self.ADAM_B1, self.ADAM_B2, self.ADAM_EPS, st)

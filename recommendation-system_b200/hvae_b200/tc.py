@@ -20,6 +20,9 @@ MAX_K_REG = 32
 def user_vectors_bf16(eng, u, B):
     d = eng.lay.d
     ub = eng.ws.get("u_bf16", (B, r8(d)), torch.bfloat16)
+    if getattr(eng, "ub_fresh", None) == (u.data_ptr(), B):       # written by the epilogue of the GEMM that produced u
+        eng.ub_fresh = None
+        return ub
     eng.lib.cast_bf16(p(u), B, d, r4(d), p(ub), r8(d), eng.stream)
     return ub
 
@@ -51,7 +54,10 @@ def score_loss_bf16(eng, batch, u, want_grad):
         c_part, l_part, w_part = ws.get("tc_c_part", (gs, B)), ws.get("tc_l_part", (gs, n_sub, B)), ws.get("tc_w_part", (gs, B))
         with eng.span("score_onepass"):
             lib.tc_score_onepass(p(ub), ld8, B, p(Eb), ld8, N, d, p(c_part), p(l_part), p(O), ldd, st)
-            lib.tc_onepass_combine(p(c_part), p(l_part), gs, n_sub, B, p(lse), p(w_part), st)
+            if not eng.fuse & 32:
+                lib.tc_onepass_combine(p(c_part), p(l_part), gs, n_sub, B, p(lse), p(w_part), st)
+        if eng.fuse & 32:        # the combination of the splits (-> lse, weights of the O partials) happens inside du_finalize_onepass
+            return lse, dot, xsum, O, (xsum, (c_part, l_part, n_sub), lse)
         return lse, dot, xsum, O, (xsum, w_part)
     if want_grad and eng.prof is None:        # two launches: the backward kernel merges the forward partials itself
         gs = int(lib.tc_grad_splits(B, N, d))
