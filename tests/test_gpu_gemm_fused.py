@@ -193,3 +193,77 @@ def test_train_steps_same_with_and_without_fused_epilogues(env, name):
     # a 1e-7 change in an activation can flip the TF32 rounding (2^-11) of an operand of the GEMMs downstream
     scale = d0.abs().max().item()
     assert (d1 - d0).abs().max().item() <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(8, 768, 200), (64, 600, 200), (512, 384, 600), (4096, 768, 768), (300, 50, 37)])
+def test_gemm_tf32_same_bits_every_launch(env, M, N, K):
+    """Fixed-order reductions everywhere (split-K partials in rank order, column sums in tile order): repeated launches -- with the
+    cache contents churned in between -- return the same bits, for the plain GEMM in the three operand layouts of a step and for the
+    fused epilogues."""
+    lib, dev = env
+    st = torch.cuda.current_stream().cuda_stream
+    ldk, ldn = _r4(K), _r4(N)
+    A, W, bias = _padded(_rand((M, K), dev, 21), ldk), _padded(_rand((N, K), dev, 22, K ** -0.5), ldk), _rand((N,), dev, 23)
+    Wt = _padded(_rand((K, N), dev, 24, K ** -0.5), ldn)
+    G = _padded(_rand((M, N), dev, 25), ldn)
+    q = _padded(_rand((M, N), dev, 26), ldn)
+    mask = (torch.rand(M, N, generator=torch.Generator().manual_seed(27)) > 0.3).to(torch.uint8).to(dev)
+    work = torch.zeros(int(lib.gemm_colsum_workspace_floats(M, N)), device=dev)
+    churn = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+
+    def run():
+        c1, c2, c3 = torch.zeros(M, ldn, device=dev), torch.zeros(M, ldn, device=dev), torch.zeros(N, ldk, device=dev)
+        c4, cs = torch.zeros(M, ldn, device=dev), torch.zeros(N, device=dev)
+        lib.gemm_tf32(M, N, K, A.data_ptr(), ldk, 1, W.data_ptr(), 1, ldk, c1.data_ptr(), ldn, bias.data_ptr(), 1.0, st)         # y = x W^T + b
+        lib.gemm_tf32(M, N, K, A.data_ptr(), ldk, 1, Wt.data_ptr(), ldn, 1, c2.data_ptr(), ldn, None, 1.0, st)                   # dx = dy W
+        lib.gemm_tf32(N, K, M, G.data_ptr(), 1, ldn, A.data_ptr(), ldk, 1, c3.data_ptr(), ldk, None, 1.0, st)                    # dW = dy^T x
+        lib.gemm_tf32_gelu_bwd(M, N, K, A.data_ptr(), ldk, 1, Wt.data_ptr(), ldn, 1, c4.data_ptr(), ldn, q.data_ptr(), mask.data_ptr(),
+                               1 / 0.7, cs.data_ptr(), work.data_ptr(), st)
+        torch.cuda.synchronize()
+        return c1, c2, c3, c4, cs
+
+    first = run()
+    for _ in range(15):
+        churn.random_(0, 255)
+        again = run()
+        for a, b in zip(first, again):
+            assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_step_and_topk_same_bits_every_run(env, precision):
+    """Two fresh runs of the same two training steps (the reference's noise) and of the evaluator's top-20: identical bits --
+    no atomics or arrival-order reductions anywhere on the path."""
+    lib, dev = env
+    from golden_util import BigCase
+    from hvae_b200.engine import DeviceCSR
+    from hvae_b200.evaluate import RecommendationEvaluator
+    from hvae_b200.model import create_hybrid_vae
+    from hvae_b200.train import VAETrainer
+    c = BigCase("d768_train")
+    churn = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+
+    def run():
+        torch.manual_seed(c.seed)
+        m = create_hybrid_vae(**c.model_kwargs(), precision=precision).to(dev)
+        tr = VAETrainer(m, dev, lr=1e-3)
+        csr = DeviceCSR.from_scipy(c.csr, dev)
+        m.train()
+        losses = []
+        for s in range(c.steps):
+            churn.random_(0, 255)
+            rows = c.rows(s)
+            n, u8 = c.noise(s), (lambda t: None if t is None else t.to(torch.uint8).to(dev).contiguous())
+            noise = dict(masks=[u8(t) for t in n["masks"]], eps=n["eps"].to(dev).contiguous(), pmask=u8(n["pmask"]))
+            tr.train_step(csr.batch(torch.tensor(rows, dtype=torch.int32, device=dev), rows), noise)
+            losses.append(tr.last_losses())
+        m.eval()
+        ev = RecommendationEvaluator(m, c.csr, {}, {}, dev)
+        val, idx = ev.topk_users(np.arange(64), 20)
+        return losses, m.engine.arena.clone(), val.clone(), idx.clone()
+
+    l0, a0, v0, i0 = run()
+    for _ in range(3):
+        l1, a1, v1, i1 = run()
+        assert l0 == l1
+        assert torch.equal(a0, a1) and torch.equal(v0, v1) and torch.equal(i0, i1)
