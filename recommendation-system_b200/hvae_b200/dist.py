@@ -188,6 +188,12 @@ class DataParallel:
         self.exchange_mode = os.environ.get("HVAE_DP_EXCHANGE", "auto")
         self.exchange = None          # "nvl" | "nccl" once decided
         self._sym = None
+        # HVAE_DP_EARLY_DENSE=1: the dense gradients from fc_mu on (fc_mu/fc_logvar, the projection MLP: ~all of the dense parameters) are
+        # final well before the end of the backward pass; they are all-reduced by NCCL on a side stream under the encoder's backward
+        # kernels and only the encoder's small tensors (ready last) travel with the dH1 rows in the step-end exchange.  Measured at N = 8
+        # (profiles/r02_ncu_summary.md section 5): the exchange shrinks 0.208 -> 0.144 ms, the NCCL kernels beside the backward pass cost
+        # the same again (3.243 vs 3.258 ms per step) -- off by default.
+        self.early_dense = os.environ.get("HVAE_DP_EARLY_DENSE", "0") == "1"
 
     # -- batch splitting -------------------------------------------------------------------------------------
     def local_rows(self, global_rows):
@@ -288,8 +294,27 @@ class DataParallel:
             self.exchange, self._sym = "nccl", None
         return self.exchange
 
+    def dense_head(self, eng) -> int:
+        """Floats of eng.gd exchanged at the end of the step (the rest was all-reduced early)."""
+        return (eng.lay.slots["fc_mu.weight"].off - eng.lay.n_w1) if self.early_dense else eng.gd.numel()
+
+    def reduce_dense_early(self, eng):
+        """Called by Engine.backward once the weight / bias gradients of fc_mu..projection are enqueued (side streams 0 and 1): their
+        all-reduce runs on its own stream beside the rest of the backward pass and is joined before the step-end exchange."""
+        if not self.early_dense:
+            return
+        tail = eng.gd[self.dense_head(eng):]
+        if not eng.concurrent:
+            dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        with eng.side(6):
+            for i in (0, 1):
+                if i < len(eng._side):
+                    torch.cuda.current_stream(eng.dev).wait_stream(eng._side[i])
+            dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.group)
+
     def exchange_grads(self, eng, batch, dpre0):
-        n = self.world * (eng.gd.numel() + self.b_max(eng.b_global) * dpre0.shape[1])
+        n = self.world * (self.dense_head(eng) + self.b_max(eng.b_global) * dpre0.shape[1])
         if self.exchange is None or (self.exchange == "nvl" and self._sym["n"] < n):
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("the gradient exchange must be set up before graph capture (run one eager step first)")
@@ -303,7 +328,7 @@ class DataParallel:
         buffers (one NVSwitch-multicast store stream), bracketed by two symmetric-memory barriers; then the same fixed-order
         sum of the dense gradients and in-place consumption of the dH1 blocks as the NCCL path."""
         from ._cabi import p
-        n_dense = eng.gd.numel()
+        n_dense = self.dense_head(eng)
         bm, B, ld = self.b_max(eng.b_global), batch.B, dpre0.shape[1]
         stride = n_dense + bm * ld
         sym = self._symmetric(eng, self.world * stride)
@@ -324,12 +349,12 @@ class DataParallel:
         weight-gradient kernel reads the gathered dH1 blocks in place.  -> (pointer to rank 0's dH1 block, rows per block,
         block stride in floats)."""
         from ._cabi import p
-        n_dense = eng.gd.numel()
+        n_dense = self.dense_head(eng)
         bm, B, ld = self.b_max(eng.b_global), batch.B, dpre0.shape[1]
         stride = n_dense + bm * ld
         ws = eng.ws
         send = ws.get("dp_send", (stride,))
-        send[:n_dense].copy_(eng.gd)
+        send[:n_dense].copy_(eng.gd[:n_dense])
         send[n_dense:n_dense + B * ld].copy_(dpre0[:B].reshape(-1))
         if B < bm:
             send[n_dense + B * ld:].zero_()

@@ -537,6 +537,8 @@ class Engine:
         if not (f_lat and f_cs):
             with self.side(1):
                 lib.colsum(p(dml), ldml, B, 2 * L, self.G("fc_ml.bias"), p(cs_ws), self.stream)
+        if self.dist is not None and dense_w1 is None:      # data parallel: these gradients are complete -> all-reduce them now, on the side
+            self.dist.reduce_dense_early(self)
         dact = ws.get(f"dact{nh - 1}", (B, r4(h[-1])))
         self.mm(B, h[-1], 2 * L, p(dml), ldml, 1, self.P("fc_mu.weight"), wm.ld, 1, p(dact), r4(h[-1]))
         ln_ws = ws.get("ln_ws", (max(lib.ln_bwd_workspace_floats(B, r4(hh)) for hh in h),))
