@@ -515,60 +515,72 @@ def _get_device(device: str | None = None) -> torch.device:
     raise RuntimeError("hvae_b200 needs a CUDA device (there is no CPU fallback)")
 
 
+class _EarlyStop:
+    """Best validation loss so far + epochs since it improved."""
+
+    def __init__(self, patience: int):
+        self.patience, self.best, self.stale = patience, float("inf"), 0
+
+    def improved(self, value: float) -> bool:
+        better = value < self.best
+        self.best, self.stale = (value, 0) if better else (self.best, self.stale + 1)
+        return better
+
+    @property
+    def exhausted(self) -> bool:
+        return self.stale >= self.patience
+
+
+def _write_history(trainer: "VAETrainer", path: Path, seconds: float) -> None:
+    """training_history.json as the reference writes it (src/ml/train.py:325-336): same keys, same rounding."""
+    doc = {k: getattr(trainer, k) for k in ("train_losses", "val_losses", "train_recon_losses", "train_kl_losses")}
+    doc["training_time_seconds"] = round(seconds, 2)
+    path.write_text(json.dumps(doc, indent=2))
+
+
+def _split_loaders(data_dir: str, batch_size: int, dev):
+    """(train loader, val loader, n_items) from the offline pipeline's files: each split keeps ONLY its own interactions."""
+    full_matrix, train_df, val_df, mappings = load_training_data(data_dir)
+    u2i, i2i = mappings["user_to_idx"], mappings["item_to_idx"]
+    loaders = [CSRLoader(_build_matrix(df, u2i, i2i, full_matrix.shape), get_user_indices_from_df(df, u2i), batch_size, shuffle, dev)
+               for df, shuffle in ((train_df, True), (val_df, False))]
+    return loaders[0], loaders[1], full_matrix.shape[1]
+
+
 def train_hybrid_vae(data_dir: str, embeddings_path: str, output_dir: str, latent_dim: int = 200,
                      hidden_dims: list[int] | None = None, batch_size: int = 512, epochs: int = 100,
                      learning_rate: float = 0.001, weight_decay: float = 0.0, beta: float = 0.2, dropout: float = 0.5,
                      use_annealing: bool = False, patience: int = 10, device: str | None = None,
                      ignore_embeddings: bool = False, precision: str | None = None) -> None:
-    """src/ml/train.py:201-342: same files in, same files out (checkpoint_epoch_{e}.pth, best_model.pth,
-    training_history.json)."""
+    """The reference's training driver as a file contract (src/ml/train.py:201-342): same inputs, same outputs
+    (checkpoint_epoch_{e}.pth, best_model.pth, training_history.json), early stopping on the validation loss."""
     dev = _get_device(device)
-    output_path = Path(output_dir)
-    output_path.mkdir(parents=True, exist_ok=True)
-    full_matrix, train_df, val_df, mappings = load_training_data(data_dir)
-    user_to_idx, item_to_idx = mappings["user_to_idx"], mappings["item_to_idx"]
-    n_items = full_matrix.shape[1]
-    train_matrix = _build_matrix(train_df, user_to_idx, item_to_idx, full_matrix.shape)
-    val_matrix = _build_matrix(val_df, user_to_idx, item_to_idx, full_matrix.shape)
-    emb_path = Path(embeddings_path)
-    embeddings, emb_item_to_idx, _ = _data.load_embeddings(embeddings_path, str(emb_path.with_name(f"{emb_path.stem}_mappings.pkl")))
-    assert emb_item_to_idx and len(emb_item_to_idx) == n_items, \
-        f"Embedding mismatch: {len(emb_item_to_idx) if emb_item_to_idx else 0} vs {n_items}"
-    if ignore_embeddings:
+    out = Path(output_dir)
+    out.mkdir(parents=True, exist_ok=True)
+    train_loader, val_loader, n_items = _split_loaders(data_dir, batch_size, dev)
+    emb_file = Path(embeddings_path)
+    embeddings, emb_items, _ = _data.load_embeddings(embeddings_path, str(emb_file.with_name(f"{emb_file.stem}_mappings.pkl")))
+    if not emb_items or len(emb_items) != n_items:
+        raise AssertionError(f"Embedding mismatch: {len(emb_items) if emb_items else 0} vs {n_items}")
+    if ignore_embeddings:          # ablation switch of the reference: random vectors of the same shape
         embeddings = np.random.normal(0, 0.01, embeddings.shape).astype(np.float32)
-    train_loader = CSRLoader(train_matrix, get_user_indices_from_df(train_df, user_to_idx), batch_size, True, dev)
-    val_loader = CSRLoader(val_matrix, get_user_indices_from_df(val_df, user_to_idx), batch_size, False, dev)
-    anneal_steps = int(len(train_loader) * epochs * 0.5)
     model = create_hybrid_vae(n_items=n_items, item_embeddings=embeddings, latent_dim=latent_dim, hidden_dims=hidden_dims,
-                              dropout=dropout, beta=beta, use_annealing=use_annealing, anneal_steps=anneal_steps,
-                              precision=precision)
+                              dropout=dropout, beta=beta, use_annealing=use_annealing,
+                              anneal_steps=int(len(train_loader) * epochs * 0.5), precision=precision)
     trainer = VAETrainer(model, dev, learning_rate, weight_decay)
-    best_val_loss, patience_counter = float("inf"), 0
-    start_time = time.time()
-    for epoch in range(epochs):
-        train_metrics = trainer.train_epoch(train_loader)
-        val_metrics = trainer.validate(val_loader)
-        trainer.train_losses.append(train_metrics["total_loss"])
-        trainer.val_losses.append(val_metrics["total_loss"])
-        trainer.train_recon_losses.append(train_metrics["recon_loss"])
-        trainer.train_kl_losses.append(train_metrics["kl_loss"])
-        logger.info("Epoch %d/%d train %.4f (recon %.4f, kl %.4f) val %.4f", epoch + 1, epochs, train_metrics["total_loss"],
-                    train_metrics["recon_loss"], train_metrics["kl_loss"], val_metrics["total_loss"])
-        is_best = val_metrics["total_loss"] < best_val_loss
-        if is_best:
-            best_val_loss, patience_counter = val_metrics["total_loss"], 0
-        else:
-            patience_counter += 1
-        trainer.save_checkpoint(output_path / f"checkpoint_epoch_{epoch + 1}.pth", epoch + 1, is_best,
-                                extra={"train_metrics": train_metrics, "val_metrics": val_metrics,
-                                       "model_config": {"n_items": n_items, "latent_dim": latent_dim, "hidden_dims": hidden_dims,
-                                                        "beta": beta, "dropout": dropout}})
-        if patience_counter >= patience:
-            logger.info("Early stopping at epoch %d", epoch + 1)
+    config = {"n_items": n_items, "latent_dim": latent_dim, "hidden_dims": hidden_dims, "beta": beta, "dropout": dropout}
+    stop, t0 = _EarlyStop(patience), time.time()
+    for epoch in range(1, epochs + 1):
+        tm, vm = trainer.train_epoch(train_loader), trainer.validate(val_loader)
+        for series, value in ((trainer.train_losses, tm["total_loss"]), (trainer.val_losses, vm["total_loss"]),
+                              (trainer.train_recon_losses, tm["recon_loss"]), (trainer.train_kl_losses, tm["kl_loss"])):
+            series.append(value)
+        logger.info("Epoch %d/%d train %.4f (recon %.4f, kl %.4f) val %.4f", epoch, epochs, tm["total_loss"], tm["recon_loss"],
+                    tm["kl_loss"], vm["total_loss"])
+        trainer.save_checkpoint(out / f"checkpoint_epoch_{epoch}.pth", epoch, stop.improved(vm["total_loss"]),
+                                extra={"train_metrics": tm, "val_metrics": vm, "model_config": config})
+        if stop.exhausted:
+            logger.info("Early stopping at epoch %d", epoch)
             break
-    training_time = time.time() - start_time
-    with open(output_path / "training_history.json", "w") as f:
-        json.dump({"train_losses": trainer.train_losses, "val_losses": trainer.val_losses,
-                   "train_recon_losses": trainer.train_recon_losses, "train_kl_losses": trainer.train_kl_losses,
-                   "training_time_seconds": round(training_time, 2)}, f, indent=2)
-    logger.info("Training complete. Best val loss %.4f in %.1fs", best_val_loss, training_time)
+    _write_history(trainer, out / "training_history.json", time.time() - t0)
+    logger.info("Training complete. Best val loss %.4f in %.1fs", stop.best, time.time() - t0)
