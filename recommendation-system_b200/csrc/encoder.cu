@@ -594,9 +594,11 @@ int hvae_ln_act_fwd(const float* pre, int B, int h, int ld, const float* gamma, 
 }
 
 // workspace: partial [nwarps = 8*blocks][2][ld] floats + stage buffer; see hvae_ln_bwd_workspace_floats
-static inline int ln_bwd_blocks(int B) { return max(1, min(74, ceil_div(B, 8))); }
+// one row per warp and trip; up to two 8-warp blocks per SM (a 4,096-row batch ran 43 us on 74 blocks: 7 dependent row trips per warp)
+static inline int ln_bwd_blocks(int B) { return max(1, min(2 * kNumSMs, ceil_div(B, 8))); }
+constexpr int kLnBwdOnePass = 74;      // up to this many partial rows are summed by one launch, more in two stages
 
-size_t hvae_ln_bwd_workspace_floats(int B, int ld) { return (size_t)ln_bwd_blocks(B) * 8 * 2 * ld; }
+size_t hvae_ln_bwd_workspace_floats(int B, int ld) { return ((size_t)ln_bwd_blocks(B) * 8 + 64) * 2 * ld; }
 
 int hvae_ln_act_bwd(const float* dact, const float* pre, const float* mean, const float* rstd, const float* gamma,
                     const float* beta, const uint8_t* mask, float keep_scale, int B, int h, int ld, float* dpre,
@@ -611,7 +613,14 @@ int hvae_ln_act_bwd(const float* dact, const float* pre, const float* mean, cons
                              dact, pre, mean, rstd, gamma, beta, mask, keep_scale, B, h, ld / 4, dpre, workspace)));
     HVAE_LAUNCH_CHECK("ln_act_bwd");
     // one partial row per block, [2*ld] wide: first ld = d(gamma), next ld = d(beta)
-    const int R = blocks;
+    int R = blocks;
+    if (R > kLnBwdOnePass) {      // first stage: 64 groups of partial rows -> 64 rows behind the partials
+        const int chunks = 64, rpc = ceil_div(R, chunks);
+        float* stage = workspace + (size_t)blocks * 8 * 2 * ld;
+        launch_pdl(colsum_chunk_kernel, dim3(ceil_div(2 * ld, 128), chunks), 128, 0, (cudaStream_t)stream, workspace, 2 * ld, R, 2 * ld, rpc, stage, 2 * ld);
+        workspace = stage;
+        R = ceil_div(R, rpc);
+    }
     if (dbeta == dgamma + ld) {   // adjacent slots of the gradient arena: one launch over both (pad columns of the partials are zero)
         launch_pdl(colsum_chunk_kernel, dim3(ceil_div(2 * ld, 64), 1), 64, 0, (cudaStream_t)stream, workspace, 2 * ld, R, 2 * ld, R, dgamma, 2 * ld);
     } else {

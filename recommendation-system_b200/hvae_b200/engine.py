@@ -548,6 +548,8 @@ class Engine:
             gk, bk = (f"encoder.{4 * i + 1}.weight", f"encoder.{4 * i + 1}.bias")
             lib.ln_act_bwd(p(dact), p(pre), p(mean), p(rstd), self.P(gk), self.P(bk), p(None if masks is None else masks[i]),
                            self.keep_scale, B, hi, ld, p(dact), self.G(gk), self.G(bk), p(ln_ws), st)   # dact becomes dpre
+            if B > 74 * 8:
+                lib.launches += 1                # (large batches: the partial d(gamma), d(beta) rows are summed in two launches)
             with self.side(1):
                 lib.colsum(p(dact), ld, B, hi, self.G(f"encoder.{4 * i}.bias"), p(cs_ws), self.stream)
             if i > 0:
