@@ -1100,7 +1100,9 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
     static bool attr_set = false;
     if (!attr_set) {
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
+        HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStatsSmem));
         HVAE_CUDA(cudaFuncSetAttribute(score_stats_kernel<MODE_TOPK, STAGES_SMEM_LIST, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1109,9 +1111,15 @@ int hvae_tc_score_topk(const void* U, int ldu, int B, const void* E, int lde, in
     }
     const dim3 grid(m_tiles, P.n_splits);
     cudaStream_t st = (cudaStream_t)stream;
-    // the list capacity is a compile-time size (register arrays): the smallest bucket that holds K
+    // the list capacity is a compile-time size (register arrays): the smallest bucket that holds K.  A list longer than K costs twice: the
+    // admission threshold is its LAST entry (more insertions) and every insertion walks the whole list -- hence buckets at the evaluation
+    // protocol's own K values (5, 10, 20: src/ml/evaluate.py k_values)
+    static const int force_kreg = getenv("HVAE_TOPK_KREG") ? atoi(getenv("HVAE_TOPK_KREG")) : 0;        // A/B runs: a larger bucket than needed
+    if (force_kreg >= K && force_kreg <= MAXK_REG) K = force_kreg;       // (P.K, the number of results written, stays)
     if (K <= 8) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 8>, grid, 192, kStatsSmem, st, tmU, tmE, P);
+    else if (K <= 12) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 12>, grid, 192, kStatsSmem, st, tmU, tmE, P);
     else if (K <= 16) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 16>, grid, 192, kStatsSmem, st, tmU, tmE, P);
+    else if (K <= 20) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 20>, grid, 192, kStatsSmem, st, tmU, tmE, P);
     else if (K <= 24) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 24>, grid, 192, kStatsSmem, st, tmU, tmE, P);
     else if (K <= MAXK_REG) launch_pdl(score_stats_kernel<MODE_TOPK, STAGES, 32>, grid, 192, kStatsSmem, st, tmU, tmE, P);
     else launch_pdl(score_stats_kernel<MODE_TOPK, STAGES_SMEM_LIST, 0>, grid, 192, kStatsSmemList, st, tmU, tmE, P);
