@@ -366,8 +366,8 @@ def kernel_spans(x, W, K, flush_buf, pk, world, ms_per_step, args):
             k.update(extra)
         kernels[name] = k
 
-    if "adam" in span_avg:
-        add("adam", span_avg["adam"], "hbm", adam_bytes)
+    if "adam" in span_avg:      # (two launches: rows of W1^T without a gradient -- beside the backward pass in the captured step -- and the rest)
+        add("adam", span_avg["adam"] + span_avg.get("adam_untouched", 0.0), "hbm", adam_bytes)
     if "score_fwd" in span_avg:
         add("score_fwd", span_avg["score_fwd"], "tensor", flops_fwd)
     if "score_bwd" in span_avg:

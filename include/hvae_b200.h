@@ -255,6 +255,16 @@ int hvae_grad_norm_finish(int64_t n_dense, const float* rownorm2, const int32_t*
 int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_params, int64_t n_w1, int ld1,
                    const int32_t* slot_of_item, const float* gsparse, const float* gdense, const hvae_step_state* state,
                    float weight_decay, float beta1, float beta2, float eps, void* stream);
+/* The same update in two calls, bit for bit: (1) the W1^T rows WITHOUT a gradient in this step -- their update needs only slot_of_item of
+ * the step's batch and the step scalars, so a step runs it beside its backward pass (2.9 GB of the optimiser's traffic off the critical
+ * path); (2) the rows with a gradient (compact row k of gsparse = item uniq_item[k], k < *n_unique <= max_rows) and the dense tensors. */
+int hvae_adam_step_untouched(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_w1, int ld1,
+                             const int32_t* slot_of_item, const hvae_step_state* state, float weight_decay, float beta1,
+                             float beta2, float eps, void* stream);
+int hvae_adam_step_touched(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_params, int64_t n_w1, int ld1,
+                           const int32_t* uniq_item, const int32_t* n_unique, int max_rows, const float* gsparse,
+                           const float* gdense, const hvae_step_state* state, float weight_decay, float beta1, float beta2,
+                           float eps, void* stream);
 /* Counter-based (Philox4x32-10) keep-masks / standard normals; counter = offset + state->noise (state may be NULL). */
 int hvae_fill_noise(uint8_t* mask, int64_t n_mask, float keep_prob, float* eps, int64_t n_eps, uint64_t seed,
                     uint64_t offset, uint32_t stream_id, const hvae_step_state* state, void* stream);

@@ -87,10 +87,14 @@ __device__ __forceinline__ void adam_one(float& p, float& m, float& v, float g, 
 
 // One thread per float4.  [0, n_w1_4): layer-1 weight W1^T whose gradient exists only for the rows listed in
 // slot_of_item (row -> compact gradient row, -1 = zero gradient); [n_w1_4, n4): dense gradient gd.
+// untouched_only: just the W1^T rows WITHOUT a gradient in this step (slot < 0).  Their update (g = 0: moments decay, the parameter moves
+// along the old momentum) needs nothing from this step's backward pass -- not even the clip coefficient -- so a step can run it beside
+// the backward kernels; adam_touched_kernel then finishes the rows with a gradient and the dense tensors.  Same arithmetic per element.
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v, int64_t n4,
                                                    int64_t n_w1_4, int ld4, const int32_t* __restrict__ slot_of_item,
                                                    const float4* __restrict__ gs, const float4* __restrict__ gd,
-                                                   const hvae_step_state* __restrict__ st, float wd, float b1, float b2, float eps) {
+                                                   const hvae_step_state* __restrict__ st, float wd, float b1, float b2, float eps,
+                                                   int untouched_only) {
     pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -98,9 +102,42 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float
     if (i < n_w1_4) {
         const int64_t row = i / ld4;
         const int slot = slot_of_item[row];
+        if (untouched_only && slot >= 0) return;
         g = slot >= 0 ? gs[(int64_t)slot * ld4 + (i - row * ld4)] : make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
         g = gd[i - n_w1_4];
+    }
+    const float clip = st->clip_coef, ss = st->step_size, bs = st->bc2_sqrt;
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    adam_one(pp.x, mm.x, vv.x, g.x, clip, wd, b1, b2, eps, ss, bs);
+    adam_one(pp.y, mm.y, vv.y, g.y, clip, wd, b1, b2, eps, ss, bs);
+    adam_one(pp.z, mm.z, vv.z, g.z, clip, wd, b1, b2, eps, ss, bs);
+    adam_one(pp.w, mm.w, vv.w, g.w, clip, wd, b1, b2, eps, ss, bs);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+}
+
+// The rows of W1^T that DO have a gradient (compact row k of gs belongs to item uniq[k], k < *n_unique) and, behind them, the dense
+// tensors.  Grid: max_rows * ld4 + (n4 - n_w1_4) threads.
+__global__ void __launch_bounds__(256) adam_touched_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v, int64_t n4,
+                                                           int64_t n_w1_4, int ld4, const int32_t* __restrict__ uniq,
+                                                           const int32_t* __restrict__ n_unique, int max_rows,
+                                                           const float4* __restrict__ gs, const float4* __restrict__ gd,
+                                                           const hvae_step_state* __restrict__ st, float wd, float b1, float b2, float eps) {
+    pdl_prologue();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_row4 = (int64_t)max_rows * ld4;
+    int64_t i;
+    float4 g;
+    if (idx < n_row4) {
+        const int k = (int)(idx / ld4);
+        if (k >= *n_unique) return;
+        i = (int64_t)uniq[k] * ld4 + (idx - (int64_t)k * ld4);
+        g = gs[idx];
+    } else {
+        const int64_t j = idx - n_row4;
+        if (j >= n4 - n_w1_4) return;
+        i = n_w1_4 + j;
+        g = gd[j];
     }
     const float clip = st->clip_coef, ss = st->step_size, bs = st->bc2_sqrt;
     float4 pp = p[i], mm = m[i], vv = v[i];
@@ -231,8 +268,35 @@ int hvae_adam_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_p
     const int64_t n4 = n_params / 4;
     launch_pdl(adam_kernel, (unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream,
         (float4*)params, (float4*)exp_avg, (float4*)exp_avg_sq, n4, n_w1 / 4, ld1 / 4, slot_of_item, (const float4*)gsparse,
-        (const float4*)gdense, state, weight_decay, beta1, beta2, eps);
+        (const float4*)gdense, state, weight_decay, beta1, beta2, eps, 0);
     HVAE_LAUNCH_CHECK("adam_step");
+    return 0;
+}
+
+// hvae_adam_step in two calls with the same result: first the W1^T rows without a gradient in this step (needs slot_of_item of the
+// step's batch and the step scalars only: may run beside the backward pass), then the rows with one (uniq / n_unique of
+// hvae_batch_transpose; at most max_rows of them) and the dense tensors.
+int hvae_adam_step_untouched(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_w1, int ld1, const int32_t* slot_of_item,
+                             const hvae_step_state* state, float weight_decay, float beta1, float beta2, float eps, void* stream) {
+    HVAE_REQUIRE(n_w1 % 4 == 0 && ld1 % 4 == 0, "adam_step_untouched: sizes must be multiples of 4");
+    if (n_w1 == 0) return 0;
+    const int64_t n4 = n_w1 / 4;
+    launch_pdl(adam_kernel, (unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream, (float4*)params, (float4*)exp_avg, (float4*)exp_avg_sq, n4,
+               n4, ld1 / 4, slot_of_item, (const float4*)nullptr, (const float4*)nullptr, state, weight_decay, beta1, beta2, eps, 1);
+    HVAE_LAUNCH_CHECK("adam_step_untouched");
+    return 0;
+}
+
+int hvae_adam_step_touched(float* params, float* exp_avg, float* exp_avg_sq, int64_t n_params, int64_t n_w1, int ld1,
+                           const int32_t* uniq_item, const int32_t* n_unique, int max_rows, const float* gsparse, const float* gdense,
+                           const hvae_step_state* state, float weight_decay, float beta1, float beta2, float eps, void* stream) {
+    HVAE_REQUIRE(n_params % 4 == 0 && n_w1 % 4 == 0 && ld1 % 4 == 0, "adam_step_touched: sizes must be multiples of 4");
+    const int64_t n4 = n_params / 4, total = (int64_t)max_rows * (ld1 / 4) + (n4 - n_w1 / 4);
+    if (total == 0) return 0;
+    launch_pdl(adam_touched_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, (float4*)params, (float4*)exp_avg,
+               (float4*)exp_avg_sq, n4, n_w1 / 4, ld1 / 4, uniq_item, n_unique, max_rows, (const float4*)gsparse, (const float4*)gdense, state,
+               weight_decay, beta1, beta2, eps);
+    HVAE_LAUNCH_CHECK("adam_step_touched");
     return 0;
 }
 

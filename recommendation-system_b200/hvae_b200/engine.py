@@ -243,6 +243,7 @@ class Engine:
         self.fuse = 0 if precision == "fp32" else int(os.environ.get("HVAE_FUSE", str(self.FUSE_DEFAULT)))
         self.ub_fresh = None
         self._loss_pending = None
+        self.adam_split = os.environ.get("HVAE_ADAM_SPLIT", "1") != "0"
         self.two_pass = os.environ.get("HVAE_TWO_PASS", "0") == "1"   # bf16 training: forward-LSE + backward launches instead of the one-pass kernel
         self.prof = None  # dict name -> [(start, stop) events] when profiling spans are enabled
         self.concurrent, self._side, self._forked = False, [], set()
@@ -257,17 +258,19 @@ class Engine:
         if not self.concurrent:
             return contextlib.nullcontext()
         while len(self._side) <= i:
-            self._side.append(torch.cuda.Stream(self.dev))
+            # stream 7 carries the bulk Adam traffic beside the backward pass: lowest priority, so that the (small, latency-bound) kernels
+            # of every other branch get SM slots as soon as they are ready instead of queueing behind its half a million blocks
+            self._side.append(torch.cuda.Stream(self.dev, priority=0 if len(self._side) == 7 else -1))
         st = self._side[i]
         st.wait_stream(torch.cuda.current_stream(self.dev))
         self._forked.add(i)
         return torch.cuda.stream(st)
 
-    def join(self, only=None):
-        """Main stream waits for every side stream used since the last join (or just for the streams in `only`)."""
+    def join(self, only=None, skip=()):
+        """Main stream waits for every side stream used since the last join (or just for the streams in `only`; never for `skip`)."""
         if self._forked:
             cur = torch.cuda.current_stream(self.dev)
-            for i in sorted(self._forked if only is None else self._forked & set(only)):
+            for i in sorted((self._forked if only is None else self._forked & set(only)) - set(skip)):
                 cur.wait_stream(self._side[i])
                 self._forked.discard(i)
 
@@ -636,9 +639,18 @@ class Engine:
             wbatch = batch if self.dist is None else self.dist.gather_batch(self, batch)
             tb = self.transpose_batch(wbatch)
         ml, u, O, oscale = self.forward_loss(batch, noise, want_grad=True)
+        if self.adam_split:
+            # Adam for the W1^T rows WITHOUT a gradient in this step (most of them: moments decay, the row moves along its momentum) needs
+            # nothing from the backward pass: its 24 B/parameter stream runs on a side stream beside the latency-bound backward kernels
+            # (NOT beside the scoring kernel: measured, that one loses more L2 bandwidth than the overlap gains)
+            with self.side(7), self.span("adam_untouched"):
+                if self.concurrent and len(self._side) > 2:
+                    torch.cuda.current_stream(self.dev).wait_stream(self._side[2])        # slot_of_item comes from the transposition
+                lib.adam_step_untouched(p(self.arena), p(self.m), p(self.v), lay.n_w1, r4(lay.hidden[0]), p(self.slot_of_item), p(self.state),
+                                        weight_decay, self.ADAM_B1, self.ADAM_B2, self.ADAM_EPS, self.stream)
         with self.span("bwd_dense"):
             self.backward(batch, noise, ml, O, oscale)
-        self.join()
+        self.join(skip=(7,))
         dpre_ptr, block_rows, block_stride = p(self.dpre0), 0, 0
         if self.dist is not None:
             with self.span("exchange"):
@@ -652,8 +664,14 @@ class Engine:
         self.join(only=(1,))
         lib.grad_norm_finish(lay.n_dense, p(rn2), p(n_unique), self.MAX_NORM, p(self.state), p(gn_ws), st)
         with self.span("adam"):
-            lib.adam_step(p(self.arena), p(self.m), p(self.v), lay.n_params, lay.n_w1, r4(lay.hidden[0]), p(self.slot_of_item), p(gs),
-                          p(self.gd), p(self.state), weight_decay, self.ADAM_B1, self.ADAM_B2, self.ADAM_EPS, st)
+            if self.adam_split:
+                self.join(only=(7,))
+                lib.adam_step_touched(p(self.arena), p(self.m), p(self.v), lay.n_params, lay.n_w1, r4(lay.hidden[0]), p(uniq), p(n_unique),
+                                      min(tb["cap"], lay.N), p(gs), p(self.gd), p(self.state), weight_decay, self.ADAM_B1, self.ADAM_B2,
+                                      self.ADAM_EPS, st)
+            else:
+                lib.adam_step(p(self.arena), p(self.m), p(self.v), lay.n_params, lay.n_w1, r4(lay.hidden[0]), p(self.slot_of_item), p(gs),
+                              p(self.gd), p(self.state), weight_decay, self.ADAM_B1, self.ADAM_B2, self.ADAM_EPS, st)
         # restores slot_of_item; a batch that did not fit its nnz bound turns the step's loss into NaN (see check_overflow)
         lib.batch_release(p(uniq), p(n_unique), wbatch.nnz_cap, p(self.slot_of_item), p(tb["overflow"]), p(self.loss_out), p(self.acc), st)
 

@@ -310,6 +310,12 @@ class VAETrainer:
         self._load_static(ent, batch)
         self._run_entry(ent, b_global)
 
+    def _capture_stream(self):
+        """High-priority capture stream: the step's critical path outranks the low-priority Adam branch (Engine.side(7))."""
+        if getattr(self, "_cap_stream", None) is None:
+            self._cap_stream = torch.cuda.Stream(self.device, priority=-1)
+        return self._cap_stream
+
     def _run_entry(self, ent, b_global):
         eng = self.model.engine
         if ent["graph"] is None:
@@ -320,7 +326,7 @@ class VAETrainer:
             l0 = eng.lib.launches
             eng.concurrent = True           # independent kernels -> parallel branches of the graph
             try:
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self._capture_stream()):
                     self._eager_step(ent["batch"], None, b_global)
             finally:
                 eng.concurrent = False
