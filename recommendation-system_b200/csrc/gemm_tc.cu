@@ -7,8 +7,10 @@
 // turns each into a few microseconds.  The fp32 ("exact") mode keeps the FFMA kernel.
 // The MMA reads both operands K-major (128B-swizzled rows of 32 floats).  An operand whose m / n axis is the
 // contiguous one in memory (the transposed uses: dX = dY W, dW = dY^T X) is TMA-loaded un-swizzled into a staging
-// area and transposed smem -> smem by the four epilogue warps, which are idle during the main loop anyway
-// (kind::tf32 does not accept MN-major shared-memory descriptors in the 128B-swizzle form: measured, it yields zeros).
+// area and transposed smem -> smem by the eight conversion warps (which also round every operand to TF32 and later run the
+// epilogue; kind::tf32 does not accept MN-major shared-memory descriptors in the 128B-swizzle form: measured, it yields zeros).
+// Epilogue: each 32 x 32 accumulator chunk goes TMEM -> registers -> a per-warp shared-memory tile -> coalesced global stores;
+// optional fused epilogues (TG_EPI_*) and bias-gradient column sums, see include/hvae_b200.h.
 #include <cstdlib>
 
 #include "common.cuh"
