@@ -530,13 +530,18 @@ def dp_parity(x, args, dev, world, rank):
 
 
 # ---- extras ----------------------------------------------------------------------------------------------------------
-def extra_c2_train(args, dev, flush_buf, lib):
-    """BASELINE.json configs[1] (All_Beauty shape, 512 users per step) on this rank's GPU alone."""
+def extra_c2_train(args, dev, flush_buf, lib, fuse=None):
+    """BASELINE.json configs[1] (All_Beauty shape, 512 users per step) on this rank's GPU alone.  fuse: HVAE_FUSE bit mask of the fused
+    GEMM epilogues for this run (None = the engine's default), so that the line carries the measured reason why they are off."""
     a2 = argparse.Namespace(**vars(args))
     x = build_train("c2", a2, dev, 1, 0)
+    if fuse is not None and x.model.engine.precision != "fp32":
+        x.model.engine.fuse = int(fuse)
     r = measure_train(x, 20, 200, dev, 1, 0, flush_buf, lib)
     out = {"workload": workload_config("c2", x.c, 1)["workload"], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
            "value_hot_l2": r["value_hot"], "gpu_launches_per_step": r["launches"] / 200, "n_gpus": 1, "steps": 200, "warmup": 20}
+    if fuse is not None:
+        out["HVAE_FUSE"] = int(x.model.engine.fuse)
     del x
     gc.collect()
     torch.cuda.empty_cache()
@@ -755,6 +760,11 @@ def main():
         extra["c2_train"] = extra_c2_train(args, dev, flush_buf, lib)
         extra.update(extra_c4(args, dev, world, rank, pk, flush_buf))
         extra["c5_sweep"] = extra_c5_sweep(args, dev, world, rank)
+        if world == 1:       # the same C2 step with every fused GEMM epilogue on (fewer launches, measured slower: DESIGN.md section 8)
+            try:
+                extra["c2_train_fused_epilogues"] = extra_c2_train(args, dev, flush_buf, lib, fuse=63)
+            except Exception as e:
+                extra["c2_train_fused_epilogues"] = {"unavailable": str(e)[:200]}
 
     if rank != 0:
         return _finish(world, dist, dev)
